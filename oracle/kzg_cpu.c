@@ -1,0 +1,752 @@
+/*
+ * oracle/kzg_cpu.c -- CPU restatement of the KZG prover hot path in portable C.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and the cpu_baseline / --impl reference legs of bench.py may load this
+ * library.  The product (kzg_b200/) never links or calls it.
+ *
+ * PARITY STATUS: unpinned at the blstrs/blst boundary (see oracle/kzg_oracle.py
+ * header): the reference's arithmetic lives in the un-vendored dependency
+ * blstrs (proxima-one fork @ b98fc83, Cargo.toml:27) -> blst, which cannot be
+ * built here (no Rust toolchain, sources absent).  This file restates the
+ * published algorithms (Montgomery arithmetic over 64-bit limbs, Jacobian G1,
+ * Pippenger bucket MSM) and follows the reference's own in-tree algorithms line
+ * by line where they exist:
+ *     serial_fft / parallel_fft     src/ft.rs:291-333 / 336-387
+ *     ifft                          src/ft.rs:115-140
+ *     Polynomial::long_division     src/polynomial.rs:193-227
+ *     Polynomial::eval              src/polynomial.rs:156-165
+ *     div_by_omega_i                src/eval_form.rs:58-84
+ *     setup                         src/lib.rs:38-46
+ * It is validated against oracle/kzg_oracle.py (pure big-int) in
+ * tests/test_oracle.py.  Label for timings: "CPU restatement (portable C), not
+ * blst assembly".
+ *
+ * Data layout = blst's: Fr = 4 x u64 LE limbs, Montgomery R = 2^256;
+ * Fp = 6 x u64 LE limbs, Montgomery R = 2^384; blst_p1 = {x,y,z} Jacobian
+ * (identity: z == 0); blst_p1_affine = {x,y} (identity: all zero).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[4]; } fr_t;
+typedef struct { uint64_t l[6]; } fp_t;
+typedef struct { fp_t x, y, z; } p1_t;
+typedef struct { fp_t x, y; } p1a_t;
+
+#define EXPORT __attribute__((visibility("default")))
+#define AINLINE static inline __attribute__((always_inline))
+
+/* ----------------------------------------------------------------------- */
+/* constants                                                                */
+/* ----------------------------------------------------------------------- */
+static const uint64_t FR_MOD[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL,
+                                   0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+static const uint64_t FR_INV = 0xfffffffeffffffffULL; /* -r^-1 mod 2^64 */
+static const uint64_t FR_ONE[4] = {0x00000001fffffffeULL, 0x5884b7fa00034802ULL,
+                                   0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}; /* R mod r */
+static const uint64_t FR_R2[4] = {0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL,
+                                  0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}; /* R^2 mod r */
+
+static const uint64_t FP_MOD[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                                   0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+static const uint64_t FP_INV = 0x89f3fffcfffcfffdULL; /* -p^-1 mod 2^64 */
+static const uint64_t FP_ONE[6] = {0x760900000002fffdULL, 0xebf4000bc40c0002ULL, 0x5f48985753c758baULL,
+                                   0x77ce585370525745ULL, 0x5c071a97a256ec6dULL, 0x15f65ec3fa80e493ULL};
+static const uint64_t FP_R2[6] = {0xf4df1f341c341746ULL, 0x0a76e6a609d104f1ULL, 0x8de5476c4c95b6d5ULL,
+                                  0x67eb88a9939d83c0ULL, 0x9a793e85b519952dULL, 0x11988fe592cae3aaULL};
+/* generator, Montgomery form */
+static const uint64_t G1X[6] = {0x5cb38790fd530c16ULL, 0x7817fc679976fff5ULL, 0x154f95c7143ba1c1ULL,
+                                0xf0ae6acdf3d0e747ULL, 0xedce6ecc21dbf440ULL, 0x120177419e0bfb75ULL};
+static const uint64_t G1Y[6] = {0xbaac93d50ce72271ULL, 0x8c22631a7918fd8eULL, 0xdd595f13570725ceULL,
+                                0x51ac582950405194ULL, 0x0e1c8c3fad0059c0ULL, 0x0bbc3efc5008a26aULL};
+
+/* ----------------------------------------------------------------------- */
+/* generic N-limb Montgomery arithmetic (N is a compile-time constant)      */
+/* ----------------------------------------------------------------------- */
+AINLINE int ge_n(const uint64_t *a, const uint64_t *m, int N) {
+    for (int i = N - 1; i >= 0; i--) {
+        if (a[i] > m[i]) return 1;
+        if (a[i] < m[i]) return 0;
+    }
+    return 1;
+}
+AINLINE uint64_t sub_n(uint64_t *r, const uint64_t *a, const uint64_t *b, int N) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < N; i++) {
+        u128 t = (u128)a[i] - b[i] - borrow;
+        r[i] = (uint64_t)t;
+        borrow = (uint64_t)(t >> 64) & 1;
+    }
+    return borrow;
+}
+AINLINE uint64_t add_n(uint64_t *r, const uint64_t *a, const uint64_t *b, int N) {
+    uint64_t carry = 0;
+    for (int i = 0; i < N; i++) {
+        u128 t = (u128)a[i] + b[i] + carry;
+        r[i] = (uint64_t)t;
+        carry = (uint64_t)(t >> 64);
+    }
+    return carry;
+}
+AINLINE void mod_add(uint64_t *r, const uint64_t *a, const uint64_t *b, const uint64_t *m, int N) {
+    uint64_t t[6];
+    uint64_t c = add_n(t, a, b, N);
+    if (c || ge_n(t, m, N)) sub_n(t, t, m, N);
+    for (int i = 0; i < N; i++) r[i] = t[i];
+}
+AINLINE void mod_sub(uint64_t *r, const uint64_t *a, const uint64_t *b, const uint64_t *m, int N) {
+    uint64_t t[6];
+    if (sub_n(t, a, b, N)) add_n(t, t, m, N);
+    for (int i = 0; i < N; i++) r[i] = t[i];
+}
+AINLINE int is_zero_n(const uint64_t *a, int N) {
+    uint64_t v = 0;
+    for (int i = 0; i < N; i++) v |= a[i];
+    return v == 0;
+}
+/* CIOS Montgomery multiplication */
+AINLINE void mont_mul(uint64_t *r, const uint64_t *a, const uint64_t *b, const uint64_t *m, uint64_t inv, int N) {
+    uint64_t t[8] = {0};
+    for (int i = 0; i < N; i++) {
+        u128 c = 0;
+        for (int j = 0; j < N; j++) {
+            c += (u128)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[N];
+        t[N] = (uint64_t)c;
+        t[N + 1] = (uint64_t)(c >> 64);
+        uint64_t q = t[0] * inv;
+        c = (u128)q * m[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < N; j++) {
+            c += (u128)q * m[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[N];
+        t[N - 1] = (uint64_t)c;
+        t[N] = t[N + 1] + (uint64_t)(c >> 64);
+    }
+    if (t[N] || ge_n(t, m, N)) sub_n(t, t, m, N);
+    for (int i = 0; i < N; i++) r[i] = t[i];
+}
+
+/* Fr */
+AINLINE void fr_mul(fr_t *r, const fr_t *a, const fr_t *b) { mont_mul(r->l, a->l, b->l, FR_MOD, FR_INV, 4); }
+AINLINE void fr_add(fr_t *r, const fr_t *a, const fr_t *b) { mod_add(r->l, a->l, b->l, FR_MOD, 4); }
+AINLINE void fr_sub(fr_t *r, const fr_t *a, const fr_t *b) { mod_sub(r->l, a->l, b->l, FR_MOD, 4); }
+AINLINE int fr_is_zero(const fr_t *a) { return is_zero_n(a->l, 4); }
+AINLINE void fr_set_one(fr_t *r) { memcpy(r->l, FR_ONE, 32); }
+AINLINE void fr_set_zero(fr_t *r) { memset(r->l, 0, 32); }
+static void fr_from_u64(fr_t *r, uint64_t v) {
+    fr_t t = {{v, 0, 0, 0}}, r2;
+    memcpy(r2.l, FR_R2, 32);
+    fr_mul(r, &t, &r2);
+}
+static void fr_to_canonical(uint64_t out[4], const fr_t *a) {
+    fr_t one = {{1, 0, 0, 0}}, t;
+    fr_mul(&t, a, &one);
+    memcpy(out, t.l, 32);
+}
+static void fr_pow_u64(fr_t *r, const fr_t *a, uint64_t e) { /* pow_vartime(&[e]) */
+    fr_t acc, base = *a;
+    fr_set_one(&acc);
+    while (e) {
+        if (e & 1) fr_mul(&acc, &acc, &base);
+        fr_mul(&base, &base, &base);
+        e >>= 1;
+    }
+    *r = acc;
+}
+static void fr_inv(fr_t *r, const fr_t *a) { /* a^(r-2) */
+    uint64_t e[4];
+    memcpy(e, FR_MOD, 32);
+    e[0] -= 2;
+    fr_t acc, base = *a;
+    fr_set_one(&acc);
+    for (int i = 0; i < 256; i++) {
+        if ((e[i >> 6] >> (i & 63)) & 1) fr_mul(&acc, &acc, &base);
+        fr_mul(&base, &base, &base);
+    }
+    *r = acc;
+}
+
+/* Fp */
+AINLINE void fp_mul(fp_t *r, const fp_t *a, const fp_t *b) { mont_mul(r->l, a->l, b->l, FP_MOD, FP_INV, 6); }
+AINLINE void fp_sqr(fp_t *r, const fp_t *a) { mont_mul(r->l, a->l, a->l, FP_MOD, FP_INV, 6); }
+AINLINE void fp_add(fp_t *r, const fp_t *a, const fp_t *b) { mod_add(r->l, a->l, b->l, FP_MOD, 6); }
+AINLINE void fp_sub(fp_t *r, const fp_t *a, const fp_t *b) { mod_sub(r->l, a->l, b->l, FP_MOD, 6); }
+AINLINE int fp_is_zero(const fp_t *a) { return is_zero_n(a->l, 6); }
+AINLINE int fp_eq(const fp_t *a, const fp_t *b) { return memcmp(a, b, sizeof(fp_t)) == 0; }
+AINLINE void fp_dbl(fp_t *r, const fp_t *a) { fp_add(r, a, a); }
+static void fp_neg(fp_t *r, const fp_t *a) {
+    if (fp_is_zero(a)) { *r = *a; return; }
+    sub_n(r->l, FP_MOD, a->l, 6);
+}
+static void fp_inv(fp_t *r, const fp_t *a) { /* a^(p-2) */
+    uint64_t e[6];
+    memcpy(e, FP_MOD, 48);
+    e[0] -= 2;
+    fp_t acc, base = *a;
+    memcpy(acc.l, FP_ONE, 48);
+    for (int i = 0; i < 384; i++) {
+        if ((e[i >> 6] >> (i & 63)) & 1) fp_mul(&acc, &acc, &base);
+        fp_sqr(&base, &base);
+    }
+    *r = acc;
+}
+static void fp_to_canonical(uint64_t out[6], const fp_t *a) {
+    fp_t one = {{1, 0, 0, 0, 0, 0}}, t;
+    fp_mul(&t, a, &one);
+    memcpy(out, t.l, 48);
+}
+
+/* ----------------------------------------------------------------------- */
+/* G1 (Jacobian; y^2 = x^3 + 4)                                             */
+/* ----------------------------------------------------------------------- */
+AINLINE int p1_is_inf(const p1_t *p) { return fp_is_zero(&p->z); }
+AINLINE void p1_set_inf(p1_t *p) { memset(p, 0, sizeof(*p)); }
+AINLINE int p1a_is_inf(const p1a_t *p) { return fp_is_zero(&p->x) && fp_is_zero(&p->y); }
+
+static void p1_double(p1_t *r, const p1_t *p) { /* dbl-2009-l */
+    if (p1_is_inf(p)) { p1_set_inf(r); return; }
+    fp_t A, B, C, D, E, F, t, X3, Y3, Z3;
+    fp_sqr(&A, &p->x);
+    fp_sqr(&B, &p->y);
+    fp_sqr(&C, &B);
+    fp_add(&t, &p->x, &B); fp_sqr(&t, &t); fp_sub(&t, &t, &A); fp_sub(&t, &t, &C); fp_dbl(&D, &t);
+    fp_dbl(&E, &A); fp_add(&E, &E, &A);
+    fp_sqr(&F, &E);
+    fp_dbl(&t, &D); fp_sub(&X3, &F, &t);
+    fp_mul(&Z3, &p->y, &p->z); fp_dbl(&Z3, &Z3);
+    fp_sub(&t, &D, &X3); fp_mul(&Y3, &E, &t);
+    fp_dbl(&C, &C); fp_dbl(&C, &C); fp_dbl(&C, &C);
+    fp_sub(&Y3, &Y3, &C);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+static void p1_add(p1_t *r, const p1_t *p, const p1_t *q) { /* add-2007-bl style */
+    if (p1_is_inf(p)) { *r = *q; return; }
+    if (p1_is_inf(q)) { *r = *p; return; }
+    fp_t Z1Z1, Z2Z2, U1, U2, S1, S2, H, Rr, HH, HHH, V, t, X3, Y3, Z3;
+    fp_sqr(&Z1Z1, &p->z); fp_sqr(&Z2Z2, &q->z);
+    fp_mul(&U1, &p->x, &Z2Z2); fp_mul(&U2, &q->x, &Z1Z1);
+    fp_mul(&S1, &p->y, &q->z); fp_mul(&S1, &S1, &Z2Z2);
+    fp_mul(&S2, &q->y, &p->z); fp_mul(&S2, &S2, &Z1Z1);
+    if (fp_eq(&U1, &U2)) {
+        if (fp_eq(&S1, &S2)) { p1_double(r, p); return; }
+        p1_set_inf(r); return;
+    }
+    fp_sub(&H, &U2, &U1); fp_sub(&Rr, &S2, &S1);
+    fp_sqr(&HH, &H); fp_mul(&HHH, &H, &HH); fp_mul(&V, &U1, &HH);
+    fp_sqr(&X3, &Rr); fp_sub(&X3, &X3, &HHH); fp_dbl(&t, &V); fp_sub(&X3, &X3, &t);
+    fp_sub(&t, &V, &X3); fp_mul(&Y3, &Rr, &t); fp_mul(&t, &S1, &HHH); fp_sub(&Y3, &Y3, &t);
+    fp_mul(&Z3, &p->z, &q->z); fp_mul(&Z3, &Z3, &H);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+static void p1_add_affine(p1_t *r, const p1_t *p, const p1a_t *q) { /* mixed add */
+    if (p1a_is_inf(q)) { *r = *p; return; }
+    if (p1_is_inf(p)) { r->x = q->x; r->y = q->y; memcpy(r->z.l, FP_ONE, 48); return; }
+    fp_t Z1Z1, U2, S2, H, Rr, HH, HHH, V, t, X3, Y3, Z3;
+    fp_sqr(&Z1Z1, &p->z);
+    fp_mul(&U2, &q->x, &Z1Z1);
+    fp_mul(&S2, &q->y, &p->z); fp_mul(&S2, &S2, &Z1Z1);
+    if (fp_eq(&p->x, &U2)) {
+        if (fp_eq(&p->y, &S2)) { p1_double(r, p); return; }
+        p1_set_inf(r); return;
+    }
+    fp_sub(&H, &U2, &p->x); fp_sub(&Rr, &S2, &p->y);
+    fp_sqr(&HH, &H); fp_mul(&HHH, &H, &HH); fp_mul(&V, &p->x, &HH);
+    fp_sqr(&X3, &Rr); fp_sub(&X3, &X3, &HHH); fp_dbl(&t, &V); fp_sub(&X3, &X3, &t);
+    fp_sub(&t, &V, &X3); fp_mul(&Y3, &Rr, &t); fp_mul(&t, &p->y, &HHH); fp_sub(&Y3, &Y3, &t);
+    fp_mul(&Z3, &p->z, &H);
+    r->x = X3; r->y = Y3; r->z = Z3;
+}
+static void p1_to_affine(p1a_t *r, const p1_t *p) {
+    if (p1_is_inf(p)) { memset(r, 0, sizeof(*r)); return; }
+    fp_t zi, zi2;
+    fp_inv(&zi, &p->z);
+    fp_sqr(&zi2, &zi);
+    fp_mul(&r->x, &p->x, &zi2);
+    fp_mul(&zi2, &zi2, &zi);
+    fp_mul(&r->y, &p->y, &zi2);
+}
+/* scalar given as 4 canonical u64 limbs */
+static void p1_mul_canon(p1_t *r, const p1_t *p, const uint64_t k[4]) {
+    p1_t acc;
+    p1_set_inf(&acc);
+    for (int i = 255; i >= 0; i--) {
+        p1_double(&acc, &acc);
+        if ((k[i >> 6] >> (i & 63)) & 1) p1_add(&acc, &acc, p);
+    }
+    *r = acc;
+}
+
+EXPORT void kzgo_g1_generator(p1_t *out) {
+    memcpy(out->x.l, G1X, 48); memcpy(out->y.l, G1Y, 48); memcpy(out->z.l, FP_ONE, 48);
+}
+EXPORT void kzgo_g1_mul(p1_t *out, const p1_t *p, const fr_t *k_mont) {
+    uint64_t k[4];
+    fr_to_canonical(k, k_mont);
+    p1_mul_canon(out, p, k);
+}
+EXPORT void kzgo_g1_add(p1_t *out, const p1_t *a, const p1_t *b) { p1_add(out, a, b); }
+EXPORT void kzgo_g1_to_affine(p1a_t *out, const p1_t *p) { p1_to_affine(out, p); }
+EXPORT void kzgo_g1_to_affine_batch(p1a_t *out, const p1_t *p, size_t n) {
+    for (size_t i = 0; i < n; i++) p1_to_affine(&out[i], &p[i]);
+}
+/* ZCash 48-byte compressed encoding of an affine point */
+EXPORT void kzgo_g1_affine_compress(uint8_t out[48], const p1a_t *a) {
+    if (p1a_is_inf(a)) { memset(out, 0, 48); out[0] = 0xc0; return; }
+    uint64_t x[6], y[6], ny[6];
+    fp_to_canonical(x, &a->x);
+    fp_to_canonical(y, &a->y);
+    sub_n(ny, FP_MOD, y, 6); /* -y */
+    int y_big = 0;           /* y > -y  <=>  y > (p-1)/2 */
+    for (int i = 5; i >= 0; i--) {
+        if (y[i] > ny[i]) { y_big = 1; break; }
+        if (y[i] < ny[i]) break;
+    }
+    for (int i = 0; i < 6; i++)
+        for (int b = 0; b < 8; b++) out[47 - (8 * i + b)] = (uint8_t)(x[i] >> (8 * b));
+    out[0] |= 0x80;
+    if (y_big) out[0] |= 0x20;
+}
+EXPORT int kzgo_g1_affine_on_curve(const p1a_t *a) {
+    if (p1a_is_inf(a)) return 1;
+    fp_t y2, x3, four = {{4, 0, 0, 0, 0, 0}}, r2;
+    memcpy(r2.l, FP_R2, 48);
+    fp_mul(&four, &four, &r2);
+    fp_sqr(&y2, &a->y);
+    fp_sqr(&x3, &a->x); fp_mul(&x3, &x3, &a->x); fp_add(&x3, &x3, &four);
+    return fp_eq(&y2, &x3);
+}
+
+/* ----------------------------------------------------------------------- */
+/* Fr vector helpers                                                         */
+/* ----------------------------------------------------------------------- */
+EXPORT void kzgo_fr_from_canonical(fr_t *out, const uint64_t *in, size_t n) {
+    fr_t r2;
+    memcpy(r2.l, FR_R2, 32);
+    for (size_t i = 0; i < n; i++) {
+        fr_t t;
+        memcpy(t.l, in + 4 * i, 32);
+        fr_mul(&out[i], &t, &r2);
+    }
+}
+EXPORT void kzgo_fr_to_canonical(uint64_t *out, const fr_t *in, size_t n) {
+    for (size_t i = 0; i < n; i++) fr_to_canonical(out + 4 * i, &in[i]);
+}
+EXPORT void kzgo_fr_mul_vec(fr_t *out, const fr_t *a, const fr_t *b, size_t n) {
+    for (size_t i = 0; i < n; i++) fr_mul(&out[i], &a[i], &b[i]);
+}
+EXPORT void kzgo_fp_mul_vec(fp_t *out, const fp_t *a, const fp_t *b, size_t n) {
+    for (size_t i = 0; i < n; i++) fp_mul(&out[i], &a[i], &b[i]);
+}
+EXPORT void kzgo_fr_inv(fr_t *out, const fr_t *a) { fr_inv(out, a); }
+
+static inline uint64_t splitmix64_at(uint64_t idx) {
+    uint64_t z = (idx + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+/* Synthetic Fr stream: element i = 4 splitmix64 outputs as a
+ * 256-bit LE integer, reduced mod r; output in Montgomery form.
+ * mode 1 = reference-style single-u64 scalars. */
+EXPORT void kzgo_fr_stream(fr_t *out, uint64_t seed, size_t start, size_t n, int mode) {
+    fr_t r2;
+    memcpy(r2.l, FR_R2, 32);
+    uint64_t base = seed << 40;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t c = base + 4 * (uint64_t)(start + i);
+        fr_t v;
+        v.l[0] = splitmix64_at(c);
+        if (mode == 1) {
+            v.l[1] = v.l[2] = v.l[3] = 0;
+        } else {
+            v.l[1] = splitmix64_at(c + 1); v.l[2] = splitmix64_at(c + 2); v.l[3] = splitmix64_at(c + 3);
+            while (ge_n(v.l, FR_MOD, 4)) sub_n(v.l, v.l, FR_MOD, 4);
+        }
+        fr_mul(&out[i], &v, &r2);
+    }
+}
+
+/* Polynomial::eval (polynomial.rs:156-165), coefficients low -> high */
+EXPORT void kzgo_poly_eval(fr_t *out, const fr_t *coeffs, size_t n, const fr_t *x) {
+    fr_t res = coeffs[n - 1];
+    for (size_t i = n - 1; i-- > 0;) {
+        fr_mul(&res, &res, x);
+        fr_add(&res, &res, &coeffs[i]);
+    }
+    *out = res;
+}
+
+/* ----------------------------------------------------------------------- */
+/* ft.rs                                                                     */
+/* ----------------------------------------------------------------------- */
+static uint32_t bitreverse(uint32_t n, uint32_t l) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < l; i++) { r = (r << 1) | (n & 1); n >>= 1; }
+    return r;
+}
+/* ft.rs:291-333 */
+static void serial_fft(fr_t *a, const fr_t *omega, uint32_t log_n) {
+    uint32_t n = 1u << log_n;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t rk = bitreverse(k, log_n);
+        if (k < rk) { fr_t t = a[rk]; a[rk] = a[k]; a[k] = t; }
+    }
+    uint32_t m = 1;
+    for (uint32_t s = 0; s < log_n; s++) {
+        fr_t w_m;
+        fr_pow_u64(&w_m, omega, (uint64_t)(n / (2 * m)));
+        for (uint32_t k = 0; k < n; k += 2 * m) {
+            fr_t w;
+            fr_set_one(&w);
+            for (uint32_t j = 0; j < m; j++) {
+                fr_t t, tmp;
+                fr_mul(&t, &a[k + j + m], &w);
+                fr_sub(&tmp, &a[k + j], &t);
+                a[k + j + m] = tmp;
+                fr_add(&a[k + j], &a[k + j], &t);
+                fr_mul(&w, &w, &w_m);
+            }
+        }
+        m *= 2;
+    }
+}
+
+typedef struct {
+    const fr_t *a; fr_t *tmp; const fr_t *omega; fr_t new_omega;
+    uint32_t log_n, log_cpus, log_new_n, j;
+} pfft_task_t;
+
+static void *pfft_worker(void *arg) { /* ft.rs:346-367 */
+    pfft_task_t *t = (pfft_task_t *)arg;
+    uint32_t num_cpus = 1u << t->log_cpus;
+    fr_t omega_j, omega_step, elt;
+    fr_pow_u64(&omega_j, t->omega, t->j);
+    fr_pow_u64(&omega_step, t->omega, (uint64_t)t->j << t->log_new_n);
+    fr_set_one(&elt);
+    for (uint32_t i = 0; i < (1u << t->log_new_n); i++) {
+        fr_t acc;
+        fr_set_zero(&acc);
+        for (uint32_t s = 0; s < num_cpus; s++) {
+            uint32_t idx = (i + (s << t->log_new_n)) & ((1u << t->log_n) - 1);
+            fr_t v;
+            fr_mul(&v, &t->a[idx], &elt);
+            fr_add(&acc, &acc, &v);
+            fr_mul(&elt, &elt, &omega_step);
+        }
+        t->tmp[i] = acc;
+        fr_mul(&elt, &elt, &omega_j);
+    }
+    serial_fft(t->tmp, &t->new_omega, t->log_new_n);
+    return NULL;
+}
+/* ft.rs:336-387 */
+static void parallel_fft(fr_t *a, const fr_t *omega, uint32_t log_n, uint32_t log_cpus) {
+    uint32_t num_cpus = 1u << log_cpus, log_new_n = log_n - log_cpus;
+    fr_t *tmp = (fr_t *)malloc(sizeof(fr_t) << log_n);
+    pfft_task_t *tasks = (pfft_task_t *)malloc(sizeof(pfft_task_t) * num_cpus);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * num_cpus);
+    fr_t new_omega;
+    fr_pow_u64(&new_omega, omega, num_cpus);
+    for (uint32_t j = 0; j < num_cpus; j++) {
+        tasks[j] = (pfft_task_t){a, tmp + ((size_t)j << log_new_n), omega, new_omega, log_n, log_cpus, log_new_n, j};
+        pthread_create(&th[j], NULL, pfft_worker, &tasks[j]);
+    }
+    for (uint32_t j = 0; j < num_cpus; j++) pthread_join(th[j], NULL);
+    uint32_t mask = num_cpus - 1;
+    for (size_t idx = 0; idx < ((size_t)1 << log_n); idx++)
+        a[idx] = tmp[((size_t)(idx & mask) << log_new_n) + (idx >> log_cpus)];
+    free(tmp); free(tasks); free(th);
+}
+/* best_fft (ft.rs:274-288): log_cpus = floor(log2(threads)); threads <= 1 ->
+ * the non-"parallel" build.  */
+static void best_fft(fr_t *a, const fr_t *omega, uint32_t log_n, int threads) {
+    uint32_t log_cpus = 0;
+    while ((2u << log_cpus) <= (uint32_t)(threads > 0 ? threads : 1)) log_cpus++;
+    if (threads <= 1 || log_n <= log_cpus) serial_fft(a, omega, log_n);
+    else parallel_fft(a, omega, log_n, log_cpus);
+}
+static void root_of_unity(fr_t *out) {
+    static const uint64_t ROU[4] = {0xb9b58d8c5f0e466aULL, 0x5b1b4c801819d7ecULL,
+                                    0x0af53ae352a31e64ULL, 0x5bf3adda19e9b27bULL};
+    memcpy(out->l, ROU, 32);
+}
+/* omega for a 2^exp domain (ft.rs:73) */
+EXPORT void kzgo_domain_omega(fr_t *out, uint32_t exp) {
+    fr_t w;
+    root_of_unity(&w);
+    for (uint32_t i = exp; i < 32; i++) fr_mul(&w, &w, &w);
+    *out = w;
+}
+/* EvaluationDomain::fft / ifft (ft.rs:111-140) */
+EXPORT int kzgo_fft(fr_t *a, uint32_t log_n, int inverse, int threads) {
+    if (log_n >= 32) return 2;
+    fr_t omega;
+    kzgo_domain_omega(&omega, log_n);
+    if (!inverse) { best_fft(a, &omega, log_n, threads); return 0; }
+    fr_t omegainv, minv, m;
+    fr_inv(&omegainv, &omega);
+    best_fft(a, &omegainv, log_n, threads);
+    fr_from_u64(&m, (uint64_t)1 << log_n);
+    fr_inv(&minv, &m);
+    for (size_t i = 0; i < ((size_t)1 << log_n); i++) fr_mul(&a[i], &a[i], &minv);
+    return 0;
+}
+
+/* ----------------------------------------------------------------------- */
+/* polynomial.rs:193-227  long_division                                      */
+/*   dividend coeffs[0..=deg_p], divisor coeffs[0..=deg_d] (degree fields    */
+/*   authoritative).  quotient must hold deg_p-deg_d+1 elements; remainder   */
+/*   (deg_p+1 elements) receives the final remainder buffer.                 */
+/*   returns 0 = remainder is zero (None), 1 = non-zero remainder (Some),    */
+/*   2 = early-out zero dividend, 3 = early-out deg_p < deg_d, -1 = divisor 0*/
+/* ----------------------------------------------------------------------- */
+static size_t compute_degree(const fr_t *c, size_t ub) {
+    size_t i = ub;
+    for (;;) {
+        if (i == 0) return 0;
+        if (!fr_is_zero(&c[i])) return i;
+        i--;
+    }
+}
+EXPORT int kzgo_long_division(fr_t *quotient, fr_t *remainder, const fr_t *p, size_t deg_p,
+                              const fr_t *d, size_t deg_d) {
+    if (deg_p == 0 && fr_is_zero(&p[0])) return 2;
+    if (deg_d == 0 && fr_is_zero(&d[0])) return -1;
+    if (deg_p < deg_d) return 3;
+    memcpy(remainder, p, sizeof(fr_t) * (deg_p + 1));
+    memset(quotient, 0, sizeof(fr_t) * (deg_p - deg_d + 1));
+    size_t rdeg = deg_p;
+    fr_t lead_inverse;
+    fr_inv(&lead_inverse, &d[deg_d]);
+    while (!(rdeg == 0 && fr_is_zero(&remainder[0])) && rdeg >= deg_d) {
+        fr_t factor;
+        fr_mul(&factor, &remainder[rdeg], &lead_inverse);
+        size_t i = rdeg - deg_d;
+        quotient[i] = factor;
+        for (size_t j = 0; j <= deg_d; j++) {
+            fr_t t;
+            fr_mul(&t, &d[j], &factor);
+            fr_sub(&remainder[i + j], &remainder[i + j], &t);
+        }
+        rdeg = compute_degree(remainder, rdeg);
+    }
+    return (rdeg == 0 && fr_is_zero(&remainder[0])) ? 0 : 1;
+}
+
+/* ----------------------------------------------------------------------- */
+/* eval_form.rs:58-84  div_by_omega_i, literal (d inversions + pow_vartime)  */
+/* `limit_j`: compute only the first limit_j outputs with j != m plus q_m if */
+/* m < limit_j_m ... used for bounded-sample timing; pass d for everything.  */
+/* ----------------------------------------------------------------------- */
+EXPORT void kzgo_div_by_omega_i(fr_t *out, const fr_t *evals, uint32_t log_d, size_t m, size_t limit_j,
+                                int do_qm) {
+    size_t d = (size_t)1 << log_d;
+    fr_t omega, omega_m, dd;
+    kzgo_domain_omega(&omega, log_d);
+    fr_pow_u64(&omega_m, &omega, m);
+    fr_from_u64(&dd, d);
+    for (size_t j = 0; j < d && j < limit_j; j++) {
+        if (j == m) {
+            if (!do_qm) continue;
+            fr_t qm, am, t;
+            fr_set_zero(&qm);
+            fr_inv(&t, &omega_m);
+            fr_mul(&am, &dd, &t);
+            for (size_t i = 0; i < d; i++) {
+                if (i == m) continue;
+                fr_t omega_i, ai, term, u;
+                fr_pow_u64(&omega_i, &omega, i);
+                fr_inv(&t, &omega_i);
+                fr_mul(&ai, &dd, &t);
+                term = evals[i];
+                fr_inv(&t, &ai);
+                fr_mul(&u, &am, &t);
+                fr_mul(&term, &term, &u);
+                fr_sub(&u, &omega_m, &omega_i);
+                fr_inv(&t, &u);
+                fr_mul(&term, &term, &t);
+                fr_add(&qm, &qm, &term);
+            }
+            out[j] = qm;
+        } else {
+            fr_t omega_j, u, t;
+            fr_pow_u64(&omega_j, &omega, j);
+            fr_sub(&u, &omega_j, &omega_m);
+            fr_inv(&t, &u);
+            fr_mul(&out[j], &evals[j], &t);
+        }
+    }
+}
+
+/* ----------------------------------------------------------------------- */
+/* lib.rs:38-46 setup (literal, sequential) and an independent-power variant */
+/* ----------------------------------------------------------------------- */
+EXPORT void kzgo_setup_g1(p1_t *gs, const fr_t *s, size_t n) {
+    uint64_t k[4];
+    fr_to_canonical(k, s);
+    if (n == 0) return;
+    kzgo_g1_generator(&gs[0]);
+    for (size_t i = 1; i < n; i++) p1_mul_canon(&gs[i], &gs[i - 1], k);
+}
+
+/* ----------------------------------------------------------------------- */
+/* G1 MSM: stands in for blstrs G1Projective::multi_exp (call sites          */
+/* coeff_form.rs:61,78,102; eval_form.rs:118,136).  Like blstrs it converts  */
+/* the points to affine and the scalars out of Montgomery form per call,     */
+/* then runs the bucket (Pippenger) method; threads split the windows and    */
+/* point ranges.                                                             */
+/* ----------------------------------------------------------------------- */
+typedef struct {
+    const p1a_t *pts; const uint64_t *sc; size_t n; int c; int nwin; int nchunk; size_t chunk;
+    p1_t *partial; /* nwin * nchunk */
+    int next; pthread_mutex_t mu;
+} msm_ctx_t;
+
+static inline uint32_t get_window(const uint64_t *k, int bit, int c) {
+    int limb = bit >> 6, off = bit & 63;
+    uint64_t v = k[limb] >> off;
+    if (off + c > 64 && limb < 3) v |= k[limb + 1] << (64 - off);
+    return (uint32_t)(v & (((uint64_t)1 << c) - 1));
+}
+static void msm_task(msm_ctx_t *ctx, int task, p1_t *buckets) {
+    int w = task / ctx->nchunk, ch = task % ctx->nchunk;
+    size_t lo = (size_t)ch * ctx->chunk, hi = lo + ctx->chunk;
+    if (hi > ctx->n) hi = ctx->n;
+    size_t nb = (size_t)1 << ctx->c;
+    for (size_t b = 0; b < nb; b++) p1_set_inf(&buckets[b]);
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t d = get_window(ctx->sc + 4 * i, w * ctx->c, ctx->c);
+        if (d) p1_add_affine(&buckets[d], &buckets[d], &ctx->pts[i]);
+    }
+    p1_t run, acc;
+    p1_set_inf(&run); p1_set_inf(&acc);
+    for (size_t b = nb - 1; b >= 1; b--) {
+        p1_add(&run, &run, &buckets[b]);
+        p1_add(&acc, &acc, &run);
+    }
+    ctx->partial[task] = acc;
+}
+static void *msm_worker(void *arg) {
+    msm_ctx_t *ctx = (msm_ctx_t *)arg;
+    p1_t *buckets = (p1_t *)malloc(sizeof(p1_t) << ctx->c);
+    for (;;) {
+        pthread_mutex_lock(&ctx->mu);
+        int t = ctx->next++;
+        pthread_mutex_unlock(&ctx->mu);
+        if (t >= ctx->nwin * ctx->nchunk) break;
+        msm_task(ctx, t, buckets);
+    }
+    free(buckets);
+    return NULL;
+}
+EXPORT void kzgo_msm_g1(p1_t *out, const p1_t *points, const fr_t *scalars, size_t n, int threads) {
+    if (threads < 1) threads = 1;
+    if (n == 0) { p1_set_inf(out); return; }
+    /* per-call prep, as blstrs does */
+    p1a_t *aff = (p1a_t *)malloc(sizeof(p1a_t) * n);
+    uint64_t *sc = (uint64_t *)malloc(32 * n);
+    { /* batch to-affine (Montgomery's trick) */
+        fp_t *pre = (fp_t *)malloc(sizeof(fp_t) * n);
+        fp_t acc;
+        memcpy(acc.l, FP_ONE, 48);
+        for (size_t i = 0; i < n; i++) {
+            pre[i] = acc;
+            if (!p1_is_inf(&points[i])) fp_mul(&acc, &acc, &points[i].z);
+        }
+        fp_t inv;
+        fp_inv(&inv, &acc);
+        for (size_t i = n; i-- > 0;) {
+            if (p1_is_inf(&points[i])) { memset(&aff[i], 0, sizeof(p1a_t)); continue; }
+            fp_t zi, zi2;
+            fp_mul(&zi, &inv, &pre[i]);
+            fp_mul(&inv, &inv, &points[i].z);
+            fp_sqr(&zi2, &zi);
+            fp_mul(&aff[i].x, &points[i].x, &zi2);
+            fp_mul(&zi2, &zi2, &zi);
+            fp_mul(&aff[i].y, &points[i].y, &zi2);
+        }
+        free(pre);
+    }
+    kzgo_fr_to_canonical(sc, scalars, n);
+    int c = 1;
+    while (((size_t)1 << (c + 3)) < n && c < 16) c++; /* c ~ log2(n) - 3 */
+    if (c < 2) c = 2;
+    msm_ctx_t ctx;
+    ctx.pts = aff; ctx.sc = sc; ctx.n = n; ctx.c = c; ctx.nwin = (255 + c - 1) / c;
+    ctx.nchunk = 1;
+    while (ctx.nwin * ctx.nchunk < 2 * threads && (n / (ctx.nchunk * 2)) >= ((size_t)1 << c)) ctx.nchunk *= 2;
+    if (threads == 1) ctx.nchunk = 1;
+    ctx.chunk = (n + ctx.nchunk - 1) / ctx.nchunk;
+    ctx.partial = (p1_t *)malloc(sizeof(p1_t) * ctx.nwin * ctx.nchunk);
+    ctx.next = 0;
+    pthread_mutex_init(&ctx.mu, NULL);
+    if (threads == 1) {
+        msm_worker(&ctx);
+    } else {
+        pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+        for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, msm_worker, &ctx);
+        for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+        free(th);
+    }
+    p1_t total;
+    p1_set_inf(&total);
+    for (int w = ctx.nwin - 1; w >= 0; w--) {
+        for (int i = 0; i < c; i++) p1_double(&total, &total);
+        for (int ch = 0; ch < ctx.nchunk; ch++) p1_add(&total, &total, &ctx.partial[w * ctx.nchunk + ch]);
+    }
+    *out = total;
+    pthread_mutex_destroy(&ctx.mu);
+    free(ctx.partial); free(aff); free(sc);
+}
+
+/* ----------------------------------------------------------------------- */
+/* Reference prover entry points restated over the pieces above.             */
+/* status: 0 ok, 1 PointNotOnPolynomial                                      */
+/* ----------------------------------------------------------------------- */
+/* coeff_form.rs:59-64 */
+EXPORT void kzgo_commit(p1a_t *out, const p1_t *gs, const fr_t *coeffs, size_t num_coeffs, int threads) {
+    p1_t c;
+    kzgo_msm_g1(&c, gs, coeffs, num_coeffs, threads);
+    p1_to_affine(out, &c);
+}
+/* coeff_form.rs:66-81 */
+EXPORT int kzgo_create_witness(p1a_t *out, const p1_t *gs, const fr_t *coeffs, size_t degree, const fr_t *x,
+                               const fr_t *y, int threads) {
+    size_t n = degree + 1;
+    fr_t *dividend = (fr_t *)malloc(sizeof(fr_t) * n);
+    fr_t *rem = (fr_t *)malloc(sizeof(fr_t) * n);
+    fr_t *psi = (fr_t *)malloc(sizeof(fr_t) * n);
+    memcpy(dividend, coeffs, sizeof(fr_t) * n);
+    fr_sub(&dividend[0], &dividend[0], y);
+    fr_t divisor[2];
+    fr_set_zero(&divisor[0]);
+    fr_sub(&divisor[0], &divisor[0], x);
+    fr_set_one(&divisor[1]);
+    int st = kzgo_long_division(psi, rem, dividend, degree, divisor, 1);
+    int ret = 0;
+    p1_t w;
+    if (st == 1 || st == 3) {
+        ret = 1; /* (_, Some(_)) */
+    } else if (st == 2 || degree == 1) { /* psi.num_coeffs() == 1 */
+        fr_t z;
+        fr_set_zero(&z);
+        kzgo_g1_mul(&w, &gs[0], st == 2 ? &z : &psi[0]);
+        p1_to_affine(out, &w);
+    } else {
+        kzgo_msm_g1(&w, gs, psi, degree, threads);
+        p1_to_affine(out, &w);
+    }
+    free(dividend); free(rem); free(psi);
+    return ret;
+}
