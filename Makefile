@@ -1,0 +1,28 @@
+# Builds kzg_b200/libkzg_b200.so (sm_100a only) and the CPU oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v
+SRC_DIR := kzg_b200/csrc
+BUILD := build
+SRCS := $(wildcard $(SRC_DIR)/*.cu)
+OBJS := $(patsubst $(SRC_DIR)/%.cu,$(BUILD)/%.o,$(SRCS))
+HDRS := $(wildcard $(SRC_DIR)/*.cuh) include/kzg_b200.h
+LIB := kzg_b200/libkzg_b200.so
+
+all: $(LIB) oracle
+
+$(BUILD)/%.o: $(SRC_DIR)/%.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS)
+
+oracle:
+	$(MAKE) -C oracle -s
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,200 @@
+"""ctypes binding of libkzg_b200.so (the C ABI declared in include/kzg_b200.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or cannot
+initialise a B200, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkzg_b200.so")
+
+KZGB_OK = 0
+KZGB_POINT_NOT_ON_POLYNOMIAL = 1
+KZGB_DEGREE_TOO_LARGE = 2
+
+
+class KZGBackendError(RuntimeError):
+    """Negative status from the C ABI (invalid argument / CUDA failure)."""
+
+
+_lib = None
+_initialised_device = None
+
+
+def load():
+    """dlopen the library (no GPU needed for this)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KZGBackendError(
+                f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); "
+                "kzg_b200 has no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.kzgb_last_error_message.restype = C.c_char_p
+        _lib.kzgb_launch_count.restype = C.c_uint64
+    return _lib
+
+
+def check(status: int) -> int:
+    if status < 0:
+        msg = load().kzgb_last_error_message().decode(errors="replace")
+        raise KZGBackendError(f"kzg_b200 status {status}: {msg}")
+    return status
+
+
+def init(device: int | None = None):
+    """kzgb_init on `device` (default: LOCAL_RANK or 0).  One process drives one GPU."""
+    global _initialised_device
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _initialised_device is None:
+        check(lib.kzgb_init(C.c_int(device)))
+        _initialised_device = device
+    elif _initialised_device != device:
+        raise KZGBackendError(f"already initialised on device {_initialised_device}")
+    return lib
+
+
+def lib():
+    if _initialised_device is None:
+        return init()
+    return _lib
+
+
+def launch_count() -> int:
+    return int(load().kzgb_launch_count())
+
+
+def ptr(a) -> C.c_void_p:
+    """Host numpy array -> void*; int -> device pointer as void*; None -> NULL."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def u64(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def microbench(mode: int, blocks_per_sm: int = 4, threads: int = 256, iters: int = 64):
+    out = (C.c_double * 3)()
+    check(lib().kzgb_microbench(C.c_int(mode), C.c_int(blocks_per_sm), C.c_int(threads), C.c_int(iters), out))
+    return {"ops_per_s": out[0], "ops_per_clk_sm": out[1], "ms": out[2]}
+
+
+def test_fr_op(a, b, op: int) -> np.ndarray:
+    a = u64(a, (-1, 4))
+    b = None if b is None else u64(b, (-1, 4))
+    out = np.empty_like(a)
+    check(lib().kzgb_test_fr_op(ptr(a), ptr(b), ptr(out), C.c_size_t(len(a)), C.c_int(op)))
+    return out
+
+
+def test_fp_op(a, b, op: int) -> np.ndarray:
+    a = u64(a, (-1, 6))
+    b = None if b is None else u64(b, (-1, 6))
+    out = np.empty_like(a)
+    check(lib().kzgb_test_fp_op(ptr(a), ptr(b), ptr(out), C.c_size_t(len(a)), C.c_int(op)))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# SRS handles and MSM
+# ---------------------------------------------------------------------------
+class SRS:
+    """Owns a kzgb_srs* (device-resident affine SRS + window-multiple table)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_jacobian(cls, points, window_bits: int = 0) -> "SRS":
+        pts = u64(points, (-1, 18))
+        h = C.c_void_p()
+        check(lib().kzgb_srs_create_g1(ptr(pts), C.c_size_t(len(pts)), C.c_int(window_bits), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_affine(cls, points, window_bits: int = 0) -> "SRS":
+        pts = u64(points, (-1, 12))
+        h = C.c_void_p()
+        check(lib().kzgb_srs_create_g1_affine(ptr(pts), C.c_size_t(len(pts)), C.c_int(window_bits), C.c_int(0),
+                                              C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_device_affine(cls, dev_ptr: int, n: int, window_bits: int = 0) -> "SRS":
+        h = C.c_void_p()
+        check(lib().kzgb_srs_create_g1_affine(C.c_void_p(dev_ptr), C.c_size_t(n), C.c_int(window_bits), C.c_int(1),
+                                              C.byref(h)))
+        return cls(h)
+
+    def __len__(self) -> int:
+        f = lib().kzgb_srs_size
+        f.restype = C.c_size_t
+        return int(f(self._h))
+
+    @property
+    def window_bits(self) -> int:
+        return int(lib().kzgb_srs_window_bits(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        f = lib().kzgb_srs_device_bytes
+        f.restype = C.c_size_t
+        return int(f(self._h))
+
+    @property
+    def device_points(self) -> int:
+        f = lib().kzgb_srs_device_points
+        f.restype = C.c_void_p
+        return int(f(self._h) or 0)
+
+    def read_affine(self, start: int = 0, count: int | None = None) -> np.ndarray:
+        count = len(self) - start if count is None else count
+        out = np.empty((count, 12), dtype=np.uint64)
+        check(lib().kzgb_srs_read_affine(self._h, C.c_size_t(start), C.c_size_t(count), ptr(out)))
+        return out
+
+    def msm(self, scalars) -> np.ndarray:
+        """Host scalars (Montgomery Fr, [m,4] u64) -> affine point (12 u64)."""
+        sc = u64(scalars, (-1, 4))
+        out = np.empty(12, dtype=np.uint64)
+        check(lib().kzgb_msm_g1(self._h, ptr(sc), C.c_size_t(len(sc)), ptr(out)))
+        return out
+
+    def msm_jacobian(self, scalars) -> np.ndarray:
+        sc = u64(scalars, (-1, 4))
+        out = np.empty(18, dtype=np.uint64)
+        check(lib().kzgb_msm_g1_jacobian(self._h, ptr(sc), C.c_size_t(len(sc)), ptr(out)))
+        return out
+
+    def msm_dev(self, d_scalars: int, m: int, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+        check(lib().kzgb_msm_g1_dev(self._h, C.c_void_p(d_scalars), C.c_size_t(m), C.c_void_p(d_out),
+                                    C.c_int(out_mode), C.c_void_p(stream)))
+
+    def close(self):
+        if self._h is not None and _lib is not None and _initialised_device is not None:
+            _lib.kzgb_srs_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def g1_combine_dev(d_partials: int, count: int, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+    check(lib().kzgb_g1_combine_dev(C.c_void_p(d_partials), C.c_uint32(count), C.c_void_p(d_out), C.c_int(out_mode),
+                                    C.c_void_p(stream)))

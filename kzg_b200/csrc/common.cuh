@@ -1,0 +1,57 @@
+// common.cuh -- library-internal plumbing: status codes, error text, launch counting.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <mutex>
+
+#include "../../include/kzg_b200.h"
+
+namespace kzg {
+
+struct Context {
+    bool initialised = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;  // library-owned stream for host-pointer entry points
+    std::recursive_mutex mu;
+    uint64_t launches = 0;
+    // pinned staging (host-pointer entry points)
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // device scratch arena (grown on demand, reused across calls)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+Context& ctx();
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
+void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr (error set)
+
+#define KZG_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return ::kzg::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define KZG_REQUIRE_INIT()                                                          \
+    do {                                                                            \
+        if (!::kzg::ctx().initialised) {                                            \
+            ::kzg::set_error("kzgb_init() has not been called");                    \
+            return KZGB_ERR_NOT_INITIALISED;                                        \
+        }                                                                           \
+    } while (0)
+
+// count + check a kernel launch
+#define KZG_LAUNCHED()                                                              \
+    do {                                                                            \
+        ::kzg::ctx().launches++;                                                    \
+        KZG_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace kzg

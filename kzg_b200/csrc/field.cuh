@@ -1,0 +1,300 @@
+// field.cuh -- BLS12-381 Fq (381-bit, 12 x u32) and Fr (255-bit, 8 x u32)
+// Montgomery arithmetic for sm_100a.
+//
+// Replaces the arithmetic the reference takes from blstrs/blst (Cargo.toml:27;
+// `Scalar` ops everywhere in src/, Fp ops inside `G1Projective::multi_exp`).
+// Because 2^256 = (2^32)^8 and 2^384 = (2^32)^12, the 32-bit-limb Montgomery
+// image of an element is bit-identical to blst's 64-bit-limb image, so blst_fr /
+// blst_fp buffers are consumed with no conversion.
+//
+// Multiplication is an operand-scanning Montgomery product over two
+// interleaved accumulators ("even"/"odd" limb alignment) so that every partial
+// product a_j*b_i lands on a (lo,hi) register pair and each accumulator is one
+// unbroken carry chain: mad.lo.cc / madc.hi.cc pairs that ptxas fuses into
+// IMAD.WIDE.U32 (+carry) on the fma pipe.  4*N^2 32-bit mads per product
+// (= 2*N^2 wide mads): 288 for Fq, 128 for Fr.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kzg {
+
+// --------------------------------------------------------------------------
+// PTX carry-chain primitives
+// --------------------------------------------------------------------------
+#define KZG_DI __device__ __forceinline__
+
+KZG_DI uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+KZG_DI uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_DI uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_DI uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+KZG_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// --------------------------------------------------------------------------
+// Field parameter packs (all values verified against the big-int oracle)
+// --------------------------------------------------------------------------
+struct FqParams {
+    static constexpr int N = 12;
+    // p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    __host__ __device__ static constexpr uint32_t mod(int i) {
+        constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                         0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    // R = 2^384 mod p (Montgomery one)
+    __host__ __device__ static constexpr uint32_t one(int i) {
+        constexpr uint32_t t[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                         0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return t[i];
+    }
+    // R^2 mod p
+    __host__ __device__ static constexpr uint32_t r2(int i) {
+        constexpr uint32_t t[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                        0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return t[i];
+    }
+};
+
+struct FrParams {
+    static constexpr int N = 8;
+    // r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    __host__ __device__ static constexpr uint32_t mod(int i) {
+        constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                        0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return t[i];
+    }
+    static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    __host__ __device__ static constexpr uint32_t one(int i) {
+        constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                        0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return t[i];
+    }
+    __host__ __device__ static constexpr uint32_t r2(int i) {
+        constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                       0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return t[i];
+    }
+};
+
+// --------------------------------------------------------------------------
+// Generic Montgomery field element
+// --------------------------------------------------------------------------
+template <class P>
+struct Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    KZG_DI static Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    KZG_DI static Fe one() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    KZG_DI static Fe r2() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    KZG_DI bool is_zero() const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) v |= l[i];
+        return v == 0;
+    }
+    KZG_DI bool operator==(const Fe& o) const {
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) v |= l[i] ^ o.l[i];
+        return v == 0;
+    }
+    KZG_DI bool operator!=(const Fe& o) const { return !(*this == o); }
+
+    // r = (a >= MOD) ? a - MOD : a      (a < 2*MOD)
+    KZG_DI void final_sub() {
+        uint32_t t[N];
+        t[0] = sub_cc(l[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(l[i], P::mod(i));
+        uint32_t borrow = subc(0, 0);  // 0xffffffff if a < MOD
+#pragma unroll
+        for (int i = 0; i < N; i++) l[i] = borrow ? l[i] : t[i];
+    }
+
+    KZG_DI friend Fe operator+(const Fe& a, const Fe& b) {
+        Fe r;
+        r.l[0] = add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+        // top limb has spare bits (381 < 384, 255 < 256): no carry out for a,b < MOD
+        r.final_sub();
+        return r;
+    }
+    KZG_DI friend Fe operator-(const Fe& a, const Fe& b) {
+        Fe r;
+        r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = subc(0, 0);  // all ones if a < b
+        r.l[0] = add_cc(r.l[0], P::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow);
+        r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1) & borrow);
+        return r;
+    }
+    KZG_DI Fe neg() const { return zero() - *this; }
+    KZG_DI Fe dbl() const { return *this + *this; }
+
+    // Montgomery product a*b/R mod MOD.
+    KZG_DI friend Fe operator*(const Fe& a, const Fe& b) {
+        uint32_t E[N], O[N];
+        // ---- i = 0: plain products, no accumulation ----
+        {
+            const uint32_t bi = b.l[0];
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                O[j] = mul_lo(a.l[j + 1], bi);
+                O[j + 1] = mul_hi(a.l[j + 1], bi);
+                E[j] = mul_lo(a.l[j], bi);
+                E[j + 1] = mul_hi(a.l[j], bi);
+            }
+            reduce_step(E, O);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const uint32_t bi = b.l[i];
+            // T/2^32: new even accumulator = old O (+ old E[1] folded into limb 0),
+            // new odd accumulator = old E >> 64.
+            uint32_t nE[N], nO[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) nE[j] = O[j];
+            nE[0] = add_cc(nE[0], E[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                nO[j] = madc_lo_cc(a.l[j + 1], bi, E[j + 2]);
+                nO[j + 1] = madc_hi_cc(a.l[j + 1], bi, E[j + 3]);
+            }
+            nO[N - 2] = madc_lo_cc(a.l[N - 1], bi, 0);
+            nO[N - 1] = madc_hi(a.l[N - 1], bi, 0);
+            nE[0] = mad_lo_cc(a.l[0], bi, nE[0]);
+            nE[1] = madc_hi_cc(a.l[0], bi, nE[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                nE[j] = madc_lo_cc(a.l[j], bi, nE[j]);
+                nE[j + 1] = madc_hi_cc(a.l[j], bi, nE[j + 1]);
+            }
+            nO[N - 1] = addc(nO[N - 1], 0);
+            reduce_step(nE, nO);
+#pragma unroll
+            for (int j = 0; j < N; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+        }
+        // result = E/2^32 + O   (E[0] == 0)
+        Fe r;
+        r.l[0] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(E[j + 1], O[j]);
+        r.l[N - 1] = addc(0, O[N - 1]);
+        r.final_sub();
+        return r;
+    }
+    KZG_DI Fe sqr() const { return (*this) * (*this); }
+
+    // E + O*2^32 += m*MOD with m chosen so that limb 0 of E becomes zero.
+    KZG_DI static void reduce_step(uint32_t* E, uint32_t* O) {
+        const uint32_t m = E[0] * P::INV;
+        O[0] = mad_lo_cc(P::mod(1), m, O[0]);
+        O[1] = madc_hi_cc(P::mod(1), m, O[1]);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+            O[j] = madc_lo_cc(P::mod(j + 1), m, O[j]);
+            O[j + 1] = madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+        }
+        O[N - 2] = madc_lo_cc(P::mod(N - 1), m, O[N - 2]);
+        O[N - 1] = madc_hi(P::mod(N - 1), m, O[N - 1]);
+        E[0] = mad_lo_cc(P::mod(0), m, E[0]);
+        E[1] = madc_hi_cc(P::mod(0), m, E[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            E[j] = madc_lo_cc(P::mod(j), m, E[j]);
+            E[j + 1] = madc_hi_cc(P::mod(j), m, E[j + 1]);
+        }
+        O[N - 1] = addc(O[N - 1], 0);
+    }
+
+    // Montgomery form <-> canonical integer limbs
+    KZG_DI Fe to_mont() const { return (*this) * r2(); }
+    KZG_DI Fe from_mont() const {
+        Fe o = zero();
+        o.l[0] = 1;
+        return (*this) * o;
+    }
+
+    // a^e for a little-endian limb exponent known at run time (vartime)
+    template <int EN>
+    KZG_DI Fe pow_limbs(const uint32_t (&e)[EN]) const {
+        Fe acc = one();
+        Fe base = *this;
+        for (int i = 0; i < EN * 32; i++) {
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * base;
+            base = base.sqr();
+        }
+        return acc;
+    }
+    KZG_DI Fe pow_u64(uint64_t e) const {
+        Fe acc = one();
+        Fe base = *this;
+        while (e) {
+            if (e & 1) acc = acc * base;
+            base = base.sqr();
+            e >>= 1;
+        }
+        return acc;
+    }
+    // Fermat inversion a^(MOD-2); inv(0) = 0.
+    __device__ __noinline__ Fe inv() const {
+        Fe acc = one();
+        Fe base = *this;
+#pragma unroll 1
+        for (int i = 0; i < N * 32; i++) {
+            if ((modm2_limb(i >> 5) >> (i & 31)) & 1) acc = acc * base;
+            base = base.sqr();
+        }
+        return acc;
+    }
+    // limb i of MOD-2 (borrow propagated at compile time)
+    __host__ __device__ static constexpr uint32_t modm2_const(int i) {
+        uint32_t borrow = 2;
+        uint32_t v = 0;
+        for (int k = 0; k <= i; k++) {
+            uint32_t m = P::mod(k);
+            v = m - borrow;
+            borrow = (m < borrow) ? 1u : 0u;
+        }
+        return v;
+    }
+    KZG_DI static uint32_t modm2_limb(int i) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) v = (i == k) ? modm2_const(k) : v;
+        return v;
+    }
+};
+
+using Fq = Fe<FqParams>;
+using Fr = Fe<FrParams>;
+
+}  // namespace kzg

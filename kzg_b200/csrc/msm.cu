@@ -1,0 +1,549 @@
+// msm.cu -- G1 multi-scalar multiplication (Pippenger) for sm_100a.
+//
+// Replaces `G1Projective::multi_exp(points, scalars)` of the blstrs fork
+// (Cargo.toml:27) at its five prover call sites: coeff_form.rs:61,78,102 and
+// eval_form.rs:118,136.  Like multi_exp it sums over min(len) pairs.
+//
+// Design (B200-first, see DESIGN.md "MSM"):
+//  * The SRS is immutable for a prover's lifetime (the prover holds
+//    &'params KZGParams, coeff_form.rs:39), so the handle stores, once, the
+//    affine table T[w][i] = 2^(c*w) * P_i for every window w (HBM is 180 GB).
+//    All windows then share ONE bucket set: no per-window reduction and no
+//    Horner doublings remain on the per-call path.
+//  * per call:  K2 scalar prep (Montgomery -> canonical, signed c-bit digits)
+//               K3 CUB radix sort of (bucket, table-index|sign) pairs
+//               K4 bucket accumulation: every thread walks a fixed-length chunk
+//                  of the sorted list with one XYZZ accumulator (mixed adds),
+//                  so the load is balanced for ANY scalar distribution
+//                  (full-width, or the reference benches' single-u64 scalars
+//                  where most digits collide into a few buckets)
+//               K4b segmented fix-up of chunk-boundary partial sums
+//               K5 bucket reduction sum_b (b+1)*B[b]: chunked running sums,
+//                  small scalar-mul per chunk, tree sum
+//               K6 XYZZ -> affine / Jacobian
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "ec.cuh"
+#include "msm.cuh"
+
+namespace kzg {
+
+// --------------------------------------------------------------------------
+// K2: scalars (Montgomery Fr) -> signed digits -> (key, value) pairs
+//   key = |d|-1 (bucket), or `nbuckets` for d == 0 (sorts to the end)
+//   val = (w*n + i) | (d < 0) << 31
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ scalars, uint32_t m, uint32_t n,
+                                                         int c, int nwin, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals,
+                                                         unsigned long long* __restrict__ zero_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t zeros = 0;
+    if (i < m) {
+        Fr s = scalars[i].from_mont();
+        const uint32_t half = 1u << (c - 1);
+        uint32_t carry = 0;
+        for (int w = 0; w < nwin; w++) {
+            int bit = w * c;
+            int limb = bit >> 5, off = bit & 31;
+            uint64_t v = 0;
+            // dynamic limb select without local-memory indexing
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k == limb) v |= (uint64_t)s.l[k];
+                if (k == limb + 1) v |= (uint64_t)s.l[k] << 32;
+            }
+            uint32_t d = (uint32_t)((v >> off) & ((1u << c) - 1)) + carry;
+            uint32_t neg = 0;
+            if (d > half) {
+                d = (1u << c) - d;
+                neg = 1;
+                carry = 1;
+            } else {
+                carry = 0;
+            }
+            uint32_t key = d ? d - 1 : half;
+            zeros += (d == 0);
+            keys[(size_t)w * m + i] = key;
+            vals[(size_t)w * m + i] = ((uint32_t)w * n + i) | (neg << 31);
+        }
+    }
+    // one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) zeros += __shfl_down_sync(0xffffffffu, zeros, o);
+    if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(zero_count, (unsigned long long)zeros);
+}
+
+// --------------------------------------------------------------------------
+// K4: chunked bucket accumulation
+// --------------------------------------------------------------------------
+constexpr uint32_t SLOT_EMPTY = 0xffffffffu;
+
+__device__ __noinline__ void xyzz_madd_rare(XYZZ& acc, const Fq& x2, const Fq& y2, bool same) {
+    if (same) acc = xyzz_dbl_affine(x2, y2);
+    else acc = XYZZ::inf();
+}
+
+// hot-path mixed add; the P == 0 cases (equal / opposite points) go out of line
+KZG_DI void madd_hot(XYZZ& acc, const Fq& x2, const Fq& y2) {
+    if (acc.is_inf()) {
+        acc.x = x2; acc.y = y2; acc.zz = Fq::one(); acc.zzz = Fq::one();
+        return;
+    }
+    Fq P = x2 * acc.zz - acc.x;
+    Fq R = y2 * acc.zzz - acc.y;
+    if (P.is_zero()) {
+        xyzz_madd_rare(acc, x2, y2, R.is_zero());
+        return;
+    }
+    Fq PP = P.sqr();
+    Fq PPP = P * PP;
+    Fq Q = acc.x * PP;
+    acc.zz = acc.zz * PP;
+    acc.zzz = acc.zzz * PPP;
+    Fq X3 = R.sqr() - PPP - Q.dbl();
+    acc.y = R * (Q - X3) - acc.y * PPP;
+    acc.x = X3;
+}
+
+struct PartialMeta {
+    uint32_t bucket;   // SLOT_EMPTY if unused
+    uint32_t is_start; // the bucket's segment begins inside the producing thread's chunk
+};
+
+__global__ void __launch_bounds__(128, 3)
+msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                      const Affine* __restrict__ table, uint64_t total, const unsigned long long* __restrict__ zero_count,
+                      uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
+                      PartialMeta* __restrict__ meta, uint32_t nthreads) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const uint64_t nvalid = total - *zero_count;
+    uint64_t start = (uint64_t)t * chunk;
+    uint64_t end = start + chunk;
+    if (end > nvalid) end = nvalid;
+    PartialMeta m0{SLOT_EMPTY, 0}, m1{SLOT_EMPTY, 0};
+    if (start < end) {
+        uint32_t cur = keys[start];
+        bool cur_started_here = (start == 0) || (keys[start - 1] != cur);
+        bool first = true;
+        XYZZ acc = XYZZ::inf();
+        // software pipeline: the next point is in flight while the current one is added
+        uint32_t v = vals[start];
+        Affine p = ldg_affine(&table[v & 0x7fffffffu]);
+        for (uint64_t pos = start; pos < end; pos++) {
+            uint32_t k = cur, vn = 0;
+            Affine pn = p;
+            bool more = pos + 1 < end;
+            if (more) {
+                k = keys[pos + 1];
+                vn = vals[pos + 1];
+                pn = ldg_affine(&table[vn & 0x7fffffffu]);
+            }
+            if (!p.is_inf()) {
+                Fq y = (v >> 31) ? p.y.neg() : p.y;
+                madd_hot(acc, p.x, y);
+            }
+            if (more && k != cur) {
+                // bucket `cur` ends inside this chunk
+                if (cur_started_here) {
+                    st_xyzz(&buckets[cur], acc);
+                } else {  // can only be the first bucket of the chunk
+                    st_xyzz(&partials[2 * (size_t)t], acc);
+                    m0 = PartialMeta{cur, 0};
+                }
+                acc = XYZZ::inf();
+                cur = k;
+                cur_started_here = true;
+                first = false;
+            }
+            v = vn;
+            p = pn;
+        }
+        bool ended_here = (end == nvalid) || (keys[end] != cur);
+        if (cur_started_here && ended_here) {
+            st_xyzz(&buckets[cur], acc);
+        } else if (first) {
+            st_xyzz(&partials[2 * (size_t)t], acc);
+            m0 = PartialMeta{cur, cur_started_here ? 1u : 0u};
+        } else {
+            st_xyzz(&partials[2 * (size_t)t + 1], acc);
+            m1 = PartialMeta{cur, 1u};  // not the first bucket => it started here
+        }
+    }
+    meta[2 * (size_t)t] = m0;
+    meta[2 * (size_t)t + 1] = m1;
+}
+
+// K4b: every run of partials of one bucket is summed by the thread that owns
+// the run's first slot (is_start); runs are contiguous up to EMPTY slots.
+__global__ void __launch_bounds__(128) msm_fixup_kernel(const XYZZ* __restrict__ partials,
+                                                        const PartialMeta* __restrict__ meta, uint32_t nslots,
+                                                        XYZZ* __restrict__ buckets) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    PartialMeta m = meta[s];
+    if (m.bucket == SLOT_EMPTY || !m.is_start) return;
+    XYZZ acc = ld_xyzz(&partials[s]);
+    for (uint32_t j = s + 1; j < nslots; j++) {
+        PartialMeta mj = meta[j];
+        if (mj.bucket == SLOT_EMPTY) continue;
+        if (mj.bucket != m.bucket || mj.is_start) break;
+        XYZZ q = ld_xyzz(&partials[j]);
+        xyzz_add(acc, q);
+    }
+    st_xyzz(&buckets[m.bucket], acc);
+}
+
+// --------------------------------------------------------------------------
+// K5: bucket reduction  S = sum_{b=0}^{nb-1} (b+1) * B[b]
+// thread k owns buckets [k*m, (k+1)*m):  T_k = sum (b-lo+1) B[b] + lo * sum B[b]
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) msm_bucket_reduce_kernel(const XYZZ* __restrict__ buckets, uint32_t nb, uint32_t m,
+                                                              XYZZ* __restrict__ out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lo = k * m;
+    if (lo >= nb) return;
+    uint32_t hi = min(lo + m, nb);
+    XYZZ run = XYZZ::inf(), acc = XYZZ::inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        XYZZ q = ld_xyzz(&buckets[b]);
+        xyzz_add(run, q);
+        xyzz_add(acc, run);
+    }
+    if (lo) {
+        XYZZ sh = xyzz_mul_small(run, lo);
+        xyzz_add(acc, sh);
+    }
+    st_xyzz(&out[k], acc);
+}
+
+// block-level tree sum: out[blockIdx] = sum of in[blockIdx*per_block ...]
+constexpr int SUM_THREADS = 128;
+__global__ void __launch_bounds__(SUM_THREADS) msm_sum_kernel(const XYZZ* __restrict__ in, uint32_t count,
+                                                              uint32_t per_block, XYZZ* __restrict__ out) {
+    __shared__ XYZZ sh[SUM_THREADS];
+    uint32_t base = blockIdx.x * per_block;
+    uint32_t lim = min(base + per_block, count);
+    XYZZ acc = XYZZ::inf();
+    for (uint32_t j = base + threadIdx.x; j < lim; j += SUM_THREADS) {
+        XYZZ q = ld_xyzz(&in[j]);
+        xyzz_add(acc, q);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SUM_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            XYZZ a = sh[threadIdx.x];
+            XYZZ b = sh[threadIdx.x + s];
+            xyzz_add(a, b);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_xyzz(&out[blockIdx.x], sh[0]);
+}
+
+// K6: result conversion.  mode 0: affine (blst_p1_affine), 1: Jacobian (blst_p1), 2: raw XYZZ
+__global__ void msm_finish_kernel(const XYZZ* __restrict__ in, void* __restrict__ out, int mode) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ p = ld_xyzz(in);
+    if (mode == 0) {
+        Affine a = xyzz_to_affine(p);
+        stg_affine((Affine*)out, a);
+    } else if (mode == 1) {
+        Jacobian j = xyzz_to_jacobian(p);
+        Jacobian* o = (Jacobian*)out;
+        stg_fq(&o->x, j.x); stg_fq(&o->y, j.y); stg_fq(&o->z, j.z);
+    } else {
+        st_xyzz((XYZZ*)out, p);
+    }
+}
+
+// sum of `count` XYZZ/Jacobian partial results (multi-GPU combine) -> finish
+__global__ void msm_combine_kernel(const XYZZ* __restrict__ in, uint32_t count, XYZZ* __restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ acc = XYZZ::inf();
+    for (uint32_t i = 0; i < count; i++) {
+        XYZZ q = ld_xyzz(&in[i]);
+        xyzz_add(acc, q);
+    }
+    st_xyzz(out, acc);
+}
+
+// --------------------------------------------------------------------------
+// SRS table precomputation: T[w][i] = 2^(c*w) * P_i, affine
+// --------------------------------------------------------------------------
+constexpr int MSM_MAX_WINDOWS = 32;
+
+__global__ void __launch_bounds__(128) msm_precompute_kernel(Affine* __restrict__ table, uint32_t n, int c, int nwin) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine base = ldg_affine(&table[i]);
+    if (base.is_inf()) {
+        for (int w = 1; w < nwin; w++) stg_affine(&table[(size_t)w * n + i], Affine::inf());
+        return;
+    }
+    Fq zarr[MSM_MAX_WINDOWS], prefix[MSM_MAX_WINDOWS];
+    Jacobian q{base.x, base.y, Fq::one()};
+    Fq accz = Fq::one();
+    prefix[0] = accz;
+    for (int w = 1; w < nwin; w++) {
+        for (int d = 0; d < c; d++) q = jac_dbl(q);
+        stg_affine(&table[(size_t)w * n + i], Affine{q.x, q.y});
+        zarr[w] = q.z;
+        accz = accz * q.z;
+        prefix[w] = accz;
+    }
+    Fq inv = accz.inv();
+    for (int w = nwin - 1; w >= 1; w--) {
+        Fq zinv = inv * prefix[w - 1];
+        inv = inv * zarr[w];
+        Fq zinv2 = zinv.sqr();
+        Affine* slot = &table[(size_t)w * n + i];
+        Fq X = ldg_fq(&slot->x), Y = ldg_fq(&slot->y);
+        stg_affine(slot, Affine{X * zinv2, Y * (zinv2 * zinv)});
+    }
+}
+
+// Jacobian (blst_p1) -> affine, batched inversion inside each thread
+constexpr int TOAFF_BATCH = 8;
+__global__ void __launch_bounds__(128) jac_to_affine_kernel(const Jacobian* __restrict__ in, Affine* __restrict__ out,
+                                                            size_t n) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * TOAFF_BATCH;
+    if (lo >= n) return;
+    size_t cnt = min((size_t)TOAFF_BATCH, n - lo);
+    Fq z[TOAFF_BATCH], prefix[TOAFF_BATCH];
+    Fq acc = Fq::one();
+#pragma unroll
+    for (int j = 0; j < TOAFF_BATCH; j++) {
+        if ((size_t)j < cnt) {
+            z[j] = ldg_fq(&in[lo + j].z);
+            prefix[j] = acc;
+            if (!z[j].is_zero()) acc = acc * z[j];
+        }
+    }
+    Fq inv = acc.inv();
+#pragma unroll
+    for (int j = TOAFF_BATCH - 1; j >= 0; j--) {
+        if ((size_t)j < cnt) {
+            if (z[j].is_zero()) {
+                stg_affine(&out[lo + j], Affine::inf());
+            } else {
+                Fq zinv = inv * prefix[j];
+                inv = inv * z[j];
+                Fq zinv2 = zinv.sqr();
+                Fq X = ldg_fq(&in[lo + j].x), Y = ldg_fq(&in[lo + j].y);
+                stg_affine(&out[lo + j], Affine{X * zinv2, Y * (zinv2 * zinv)});
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------
+int msm_choose_window(size_t n) {
+    // cost model in Fq multiplications: n*W mixed adds (10) + 2^(c-1) buckets * (2 full adds (14) + amortised
+    // scalar-mul/tree (~14)); table memory W*n*96 B is capped at ~1/4 of HBM.
+    int best = 8;
+    double best_cost = 1e300;
+    for (int c = 6; c <= 22; c++) {
+        int w = (256 + c - 1) / c;
+        if (w > MSM_MAX_WINDOWS) continue;
+        double cost = (double)n * w * 10.0 + (double)(1u << (c - 1)) * 42.0;
+        if ((double)n * w * 96.0 > 40e9) continue;
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int srs_build_table(kzgb_srs* s, cudaStream_t stream) {
+    // s->table[0..n) already holds the affine base points
+    if (s->nwin > 1) {
+        msm_precompute_kernel<<<div_up(s->n, 128), 128, 0, stream>>>(s->table, (uint32_t)s->n, s->c, s->nwin);
+        KZG_LAUNCHED();
+    }
+    return KZGB_OK;
+}
+
+int srs_alloc(kzgb_srs** out, size_t n, int c) {
+    if (n == 0 || n > ((size_t)1 << 26)) {
+        set_error("srs: n = %zu out of range (1 .. 2^26)", n);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    kzgb_srs* s = new kzgb_srs();
+    s->n = n;
+    s->c = c > 0 ? c : msm_choose_window(n);
+    if (s->c < 2) s->c = 2;
+    if (s->c > 24) s->c = 24;
+    s->nwin = (256 + s->c - 1) / s->c;
+    if (s->nwin > MSM_MAX_WINDOWS) {
+        set_error("srs: window %d gives %d windows (max %d)", s->c, s->nwin, MSM_MAX_WINDOWS);
+        delete s;
+        return KZGB_ERR_INVALID_ARG;
+    }
+    cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->nwin * n * sizeof(Affine));
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(e, "cudaMalloc(srs table)", __FILE__, __LINE__);
+    }
+    *out = s;
+    return KZGB_OK;
+}
+
+void srs_free(kzgb_srs* s) {
+    if (!s) return;
+    if (s->table) cudaFree(s->table);
+    if (s->work) cudaFree(s->work);
+    delete s;
+}
+
+// Layout of the per-SRS work area for an MSM over up to n scalars
+struct MsmPlan {
+    size_t total;       // n_scalars * nwin
+    uint32_t nb;        // buckets
+    uint32_t chunk, nthreads, nslots;
+    uint32_t red_m, red_count;
+    size_t off_keys0, off_keys1, off_vals0, off_vals1, off_zero, off_buckets, off_partials, off_meta, off_red0,
+        off_red1, off_result, off_cub, cub_bytes, bytes;
+};
+
+static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
+    Context& c = ctx();
+    p.total = m * (size_t)s->nwin;
+    p.nb = 1u << (s->c - 1);
+    // threads: a whole number of waves of (SMs * 3 blocks * 128 threads)
+    size_t wave = (size_t)c.sm_count * 3 * 128;
+    size_t target_chunk = 48;
+    size_t waves = (p.total + wave * target_chunk - 1) / (wave * target_chunk);
+    if (waves < 1) waves = 1;
+    size_t nthreads = waves * wave;
+    size_t chunk = (p.total + nthreads - 1) / nthreads;
+    if (chunk < 8) {  // tiny problems: fewer threads
+        chunk = 8;
+        nthreads = (p.total + chunk - 1) / chunk;
+    }
+    p.chunk = (uint32_t)chunk;
+    p.nthreads = (uint32_t)nthreads;
+    p.nslots = 2 * p.nthreads;
+    p.red_m = p.nb >= 32 ? 32 : p.nb;
+    p.red_count = (p.nb + p.red_m - 1) / p.red_m;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    p.off_keys0 = take(p.total * 4);
+    p.off_keys1 = take(p.total * 4);
+    p.off_vals0 = take(p.total * 4);
+    p.off_vals1 = take(p.total * 4);
+    p.off_zero = take(8);
+    p.off_buckets = take((size_t)p.nb * sizeof(XYZZ));
+    p.off_partials = take((size_t)p.nslots * sizeof(XYZZ));
+    p.off_meta = take((size_t)p.nslots * sizeof(PartialMeta));
+    p.off_red0 = take((size_t)p.red_count * sizeof(XYZZ));
+    p.off_red1 = take((size_t)(p.red_count / 64 + 2) * sizeof(XYZZ));
+    p.off_result = take(sizeof(XYZZ) * 2);
+    p.cub_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, p.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, p.total, 0, s->c);
+    if (e != cudaSuccess) return cuda_fail(e, "cub SortPairs size query", __FILE__, __LINE__);
+    p.off_cub = take(p.cub_bytes);
+    p.bytes = o;
+    return KZGB_OK;
+}
+
+// Runs the MSM of the first m table points against d_scalars (device, Montgomery Fr).
+// The XYZZ result is left at *d_result_xyzz (inside the SRS work area).
+int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, const XYZZ** d_result_xyzz) {
+    if (m > s->n) {
+        set_error("msm: %zu scalars but the SRS holds %zu points", m, s->n);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    MsmPlan p;
+    int st = msm_plan(s, m ? m : 1, p);
+    if (st) return st;
+    if (p.bytes > s->work_bytes) {
+        if (s->work) {
+            KZG_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(s->work);
+            s->work = nullptr;
+            s->work_bytes = 0;
+        }
+        KZG_CUDA(cudaMalloc(&s->work, p.bytes));
+        s->work_bytes = p.bytes;
+    }
+    char* w = (char*)s->work;
+    XYZZ* result = (XYZZ*)(w + p.off_result);
+    *d_result_xyzz = result;
+    if (m == 0) {
+        KZG_CUDA(cudaMemsetAsync(result, 0, sizeof(XYZZ), stream));
+        return KZGB_OK;
+    }
+    uint32_t* keys0 = (uint32_t*)(w + p.off_keys0);
+    uint32_t* keys1 = (uint32_t*)(w + p.off_keys1);
+    uint32_t* vals0 = (uint32_t*)(w + p.off_vals0);
+    uint32_t* vals1 = (uint32_t*)(w + p.off_vals1);
+    unsigned long long* zero = (unsigned long long*)(w + p.off_zero);
+    XYZZ* buckets = (XYZZ*)(w + p.off_buckets);
+    XYZZ* partials = (XYZZ*)(w + p.off_partials);
+    PartialMeta* meta = (PartialMeta*)(w + p.off_meta);
+    XYZZ* red0 = (XYZZ*)(w + p.off_red0);
+    XYZZ* red1 = (XYZZ*)(w + p.off_red1);
+
+    KZG_CUDA(cudaMemsetAsync(zero, 0, 8, stream));
+    KZG_CUDA(cudaMemsetAsync(buckets, 0, (size_t)p.nb * sizeof(XYZZ), stream));
+    msm_digits_kernel<<<div_up(m, 256), 256, 0, stream>>>((const Fr*)d_scalars, (uint32_t)m, (uint32_t)s->n, s->c,
+                                                          s->nwin, keys0, vals0, zero);
+    KZG_LAUNCHED();
+    size_t cub_bytes = p.cub_bytes;
+    KZG_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cub_bytes, keys0, keys1, vals0, vals1, p.total, 0, s->c,
+                                             stream));
+    ctx().launches += 4;  // CUB onesweep: histogram + scan + passes (library kernels; approximate count)
+    msm_accumulate_kernel<<<div_up(p.nthreads, 128), 128, 0, stream>>>(keys1, vals1, s->table, p.total, zero, p.chunk,
+                                                                      buckets, partials, meta, p.nthreads);
+    KZG_LAUNCHED();
+    msm_fixup_kernel<<<div_up(p.nslots, 128), 128, 0, stream>>>(partials, meta, p.nslots, buckets);
+    KZG_LAUNCHED();
+    msm_bucket_reduce_kernel<<<div_up(p.red_count, 64), 64, 0, stream>>>(buckets, p.nb, p.red_m, red0);
+    KZG_LAUNCHED();
+    // tree sum red0[0..red_count) -> result (ping-pong red1 / red0)
+    uint32_t count = p.red_count;
+    XYZZ* src = red0;
+    XYZZ* bufs[2] = {red1, red0};
+    int which = 0;
+    if (count == 1) KZG_CUDA(cudaMemcpyAsync(result, src, sizeof(XYZZ), cudaMemcpyDeviceToDevice, stream));
+    while (count > 1) {
+        const uint32_t per_block = 256;
+        uint32_t blocks = div_up(count, per_block);
+        XYZZ* o = (blocks == 1) ? result : bufs[which];
+        msm_sum_kernel<<<blocks, SUM_THREADS, 0, stream>>>(src, count, per_block, o);
+        KZG_LAUNCHED();
+        count = blocks;
+        src = o;
+        which ^= 1;
+    }
+    return KZGB_OK;
+}
+
+int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream) {
+    msm_finish_kernel<<<1, 32, 0, stream>>>(d_xyzz, d_out, mode);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+int msm_combine(const void* d_partials_xyzz, uint32_t count, void* d_out_xyzz, cudaStream_t stream) {
+    msm_combine_kernel<<<1, 32, 0, stream>>>((const XYZZ*)d_partials_xyzz, count, (XYZZ*)d_out_xyzz);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+int jac_to_affine_dev(const void* d_jac, void* d_aff, size_t n, cudaStream_t stream) {
+    size_t threads = (n + TOAFF_BATCH - 1) / TOAFF_BATCH;
+    jac_to_affine_kernel<<<div_up(threads, 128), 128, 0, stream>>>((const Jacobian*)d_jac, (Affine*)d_aff, n);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+}  // namespace kzg
