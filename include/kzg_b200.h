@@ -70,6 +70,44 @@ KZGB_API uint64_t kzgb_launch_count(void);
  * out[0] = ops/s, out[1] = ops per clock per SM, out[2] = ms of the last repetition. */
 KZGB_API int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double* out);
 
+/* ---- SRS handles (KZGParams.gs, lib.rs:14-19; created once per prover) ----- */
+/* Uploads the G1 half of KZGParams (Vec<G1Projective> == contiguous blst_p1), converts it to affine ONCE (the
+ * reference's multi_exp redoes this conversion on every call) and precomputes the window-multiple table
+ * T[w][i] = 2^(c*w) * gs[i].  window_bits = 0 lets the library choose c from n. */
+KZGB_API int kzgb_srs_create_g1(const kzgb_p1* points, size_t n, int window_bits, kzgb_srs** out);
+/* Same from affine points (host pointer, or device pointer when on_device != 0). */
+KZGB_API int kzgb_srs_create_g1_affine(const kzgb_p1_affine* points, size_t n, int window_bits, int on_device,
+                                       kzgb_srs** out);
+KZGB_API int kzgb_srs_destroy(kzgb_srs* srs);
+KZGB_API size_t kzgb_srs_size(const kzgb_srs* srs);
+KZGB_API int kzgb_srs_window_bits(const kzgb_srs* srs);
+KZGB_API size_t kzgb_srs_device_bytes(const kzgb_srs* srs);
+KZGB_API const void* kzgb_srs_device_points(const kzgb_srs* srs); /* device ptr to n affine points */
+KZGB_API int kzgb_srs_read_affine(const kzgb_srs* srs, size_t start, size_t count, kzgb_p1_affine* out);
+/* Synthetic SRS built on the device from a KNOWN secret (benchmarks/tests):
+ * kind 0: gs[i] = s^i*G, the points lib.rs:38-46 `setup` produces;
+ * kind 1: L_i(s)*G in natural omega^i order, the points eval_form.rs:254-280 `compute_lagrange_basis` produces
+ *         (total must be a power of two).  Only [first, first+count) of the size-`total` SRS is generated,
+ *         so each rank of a multi-GPU job builds its own shard. */
+KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, size_t first, size_t count,
+                               int window_bits, kzgb_srs** out);
+
+/* ---- G1 MSM: replaces G1Projective::multi_exp(gs[..m], scalars) ---------------
+ * reference call sites: coeff_form.rs:61 (commit), :78 (create_witness), :102 (create_witness_batched),
+ * eval_form.rs:118 (commit), :136 (create_witness).  Uses the first m points of the SRS (m <= n), as the
+ * reference slices gs[..num_coeffs] (coeff_form.rs:60,77,101).  Scalars are Montgomery-form blst_fr. */
+KZGB_API int kzgb_msm_g1(kzgb_srs* srs, const kzgb_fr* scalars, size_t m, kzgb_p1_affine* out);   /* + .to_affine() (coeff_form.rs:63) */
+KZGB_API int kzgb_msm_g1_jacobian(kzgb_srs* srs, const kzgb_fr* scalars, size_t m, kzgb_p1* out); /* G1Projective result */
+/* Device-pointer variant.  out_mode: 0 affine (96 B), 1 Jacobian (144 B), 2 raw XYZZ partial sum (192 B). */
+KZGB_API int kzgb_msm_g1_dev(kzgb_srs* srs, const void* d_scalars, size_t m, void* d_out, int out_mode, void* stream);
+/* Multi-GPU combine: sums `count` raw XYZZ partial sums (gathered from the ranks) into one point. */
+KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream);
+
+/* ---- synthetic inputs: splitmix64 Fr stream, Montgomery form, on the device ----
+ * element i of stream `seed` = 4 consecutive outputs as a 256-bit LE integer mod r (mode 0), or a single
+ * u64 (mode 1, the distribution of benches/commit_coeff_form.rs:16-20). */
+KZGB_API int kzgb_fr_stream_dev(void* d_out, uint64_t seed, uint64_t start, size_t n, int mode, void* stream);
+
 /* ---- test hooks: element-wise device field arithmetic on host vectors ------- */
 /* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1, 4 to_mont(a), 5 from_mont(a), 6 a^2 (b may be NULL for op >= 3).
  * Pins the device Fr/Fp arithmetic (which replaces blst's, Cargo.toml:27) against the oracle. */

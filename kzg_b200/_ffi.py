@@ -198,3 +198,34 @@ class SRS:
 def g1_combine_dev(d_partials: int, count: int, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
     check(lib().kzgb_g1_combine_dev(C.c_void_p(d_partials), C.c_uint32(count), C.c_void_p(d_out), C.c_int(out_mode),
                                     C.c_void_p(stream)))
+
+
+def srs_generate(kind: int, secret, total: int, first: int = 0, count: int | None = None, window_bits: int = 0) -> SRS:
+    """Synthetic SRS from a known secret, built on the device.  kind 0: s^i*G (lib.rs:38-46);
+    kind 1: Lagrange L_i(s)*G (eval_form.rs:254-280)."""
+    count = total - first if count is None else count
+    sec = u64(secret, (4,))
+    h = C.c_void_p()
+    check(lib().kzgb_srs_generate(C.c_int(kind), ptr(sec), C.c_size_t(total), C.c_size_t(first), C.c_size_t(count),
+                                  C.c_int(window_bits), C.byref(h)))
+    return SRS(h)
+
+
+def fr_stream_dev(d_out: int, seed: int, n: int, start: int = 0, mode: int = 0, stream: int = 0) -> None:
+    check(lib().kzgb_fr_stream_dev(C.c_void_p(d_out), C.c_uint64(seed), C.c_uint64(start), C.c_size_t(n), C.c_int(mode),
+                                   C.c_void_p(stream)))
+
+
+def profile_enable(on: bool = True) -> None:
+    check(lib().kzgb_profile_enable(C.c_int(int(on))))
+
+
+def profile_read() -> dict:
+    """{stage_name: (sum_ms, count)} since the last read (synchronises the device)."""
+    l = lib()
+    n = int(l.kzgb_profile_stage_count())
+    sums = (C.c_double * n)()
+    cnts = (C.c_uint64 * n)()
+    check(l.kzgb_profile_read(sums, cnts))
+    l.kzgb_profile_stage_name.restype = C.c_char_p
+    return {l.kzgb_profile_stage_name(i).decode(): (sums[i], int(cnts[i])) for i in range(n) if cnts[i]}

@@ -1,5 +1,6 @@
 // api_core.cu -- lifecycle, error reporting, scratch/pinned arenas.
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -61,9 +62,66 @@ void* pinned_reserve(size_t bytes) {
     return c.pinned;
 }
 
+// ---- stage timer ----
+struct StageRec { int stage; cudaEvent_t a, b; };
+static bool g_prof = false;
+static std::vector<StageRec> g_recs;
+static std::vector<cudaEvent_t> g_free_events;
+static cudaEvent_t g_open[ST_COUNT];
+
+static cudaEvent_t get_event() {
+    if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void stage_begin(int stage, cudaStream_t stream) {
+    if (!g_prof) return;
+    cudaEvent_t e = get_event();
+    cudaEventRecord(e, stream);
+    g_open[stage] = e;
+}
+void stage_end(int stage, cudaStream_t stream) {
+    if (!g_prof || !g_open[stage]) return;
+    cudaEvent_t e = get_event();
+    cudaEventRecord(e, stream);
+    g_recs.push_back(StageRec{stage, g_open[stage], e});
+    g_open[stage] = nullptr;
+}
+
 }  // namespace kzg
 
 using namespace kzg;
+
+extern "C" KZGB_API int kzgb_profile_enable(int on) {
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    g_prof = on != 0;
+    return KZGB_OK;
+}
+// Synchronises the device, adds every recorded stage interval into sum_ms[stage] / counts[stage]
+// (arrays of at least kzgb_profile_stage_count() entries, zeroed by the caller) and clears the records.
+extern "C" KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_CUDA(cudaDeviceSynchronize());
+    for (auto& r : g_recs) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            if (sum_ms) sum_ms[r.stage] += ms;
+            if (counts) counts[r.stage] += 1;
+        }
+        g_free_events.push_back(r.a);
+        g_free_events.push_back(r.b);
+    }
+    g_recs.clear();
+    return KZGB_OK;
+}
+extern "C" KZGB_API int kzgb_profile_stage_count(void) { return ST_COUNT; }
+extern "C" KZGB_API const char* kzgb_profile_stage_name(int s) {
+    static const char* names[ST_COUNT] = {"msm_digits", "msm_sort", "msm_accumulate", "msm_fixup", "msm_bucket_reduce",
+                                          "msm_finish", "ntt", "scan", "div_by_omega", "interpolate", "batch_div"};
+    return (s >= 0 && s < ST_COUNT) ? names[s] : "";
+}
 
 extern "C" {
 

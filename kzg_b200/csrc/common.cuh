@@ -52,6 +52,20 @@ void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr
         KZG_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// ---- stage timer: CUDA events around each pipeline stage, on the launching stream ----
+// (bench.py's roofline needs the dominant kernel's duration measured live, outside any profiler)
+enum Stage {
+    ST_MSM_DIGITS = 0, ST_MSM_SORT, ST_MSM_ACCUMULATE, ST_MSM_FIXUP, ST_MSM_BUCKET_REDUCE, ST_MSM_FINISH,
+    ST_NTT, ST_SCAN, ST_DIV_OMEGA, ST_INTERP, ST_BATCH_DIV, ST_COUNT
+};
+void stage_begin(int stage, cudaStream_t stream);
+void stage_end(int stage, cudaStream_t stream);
+struct StageScope {
+    int stage; cudaStream_t stream;
+    StageScope(int s, cudaStream_t st) : stage(s), stream(st) { stage_begin(s, st); }
+    ~StageScope() { stage_end(stage, stream); }
+};
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace kzg

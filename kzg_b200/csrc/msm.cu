@@ -175,24 +175,61 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
     meta[2 * (size_t)t + 1] = m1;
 }
 
-// K4b: every run of partials of one bucket is summed by the thread that owns
-// the run's first slot (is_start); runs are contiguous up to EMPTY slots.
-__global__ void __launch_bounds__(128) msm_fixup_kernel(const XYZZ* __restrict__ partials,
-                                                        const PartialMeta* __restrict__ meta, uint32_t nslots,
-                                                        XYZZ* __restrict__ buckets) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslots) return;
-    PartialMeta m = meta[s];
-    if (m.bucket == SLOT_EMPTY || !m.is_start) return;
-    XYZZ acc = ld_xyzz(&partials[s]);
-    for (uint32_t j = s + 1; j < nslots; j++) {
-        PartialMeta mj = meta[j];
+// K4b: hierarchical segmented reduction of the chunk-boundary partial sums.
+// The slot list (2 per producing thread, in sorted-bucket order) is cut into
+// runs: a run starts at a slot with is_start and continues over following
+// slots of the same bucket (EMPTY slots are skipped).  Each thread owns FIX_F
+// consecutive slots; runs that start and end inside its range are final and go
+// to buckets[]; the (at most two) runs that cross its range boundary become
+// the next level's slots.  Every level shrinks the list FIX_F/2-fold, so a
+// bucket holding half of all points (reference-style u64 scalars) costs
+// O(log) levels instead of one thread walking thousands of partials.
+constexpr uint32_t FIX_F = 32;
+
+__global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
+                                                              const PartialMeta* __restrict__ min_, uint32_t nslots_in,
+                                                              XYZZ* __restrict__ buckets, XYZZ* __restrict__ pout,
+                                                              PartialMeta* __restrict__ mout, uint32_t nthreads) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    uint32_t lo = t * FIX_F, hi = min(lo + FIX_F, nslots_in);
+    const bool last_thread = hi >= nslots_in;
+    PartialMeta m0{SLOT_EMPTY, 0}, m1{SLOT_EMPTY, 0};
+    XYZZ acc = XYZZ::inf();
+    uint32_t cur = SLOT_EMPTY, cur_start = 0;
+    bool flushed_any = false;
+    for (uint32_t j = lo; j < hi; j++) {
+        PartialMeta mj = min_[j];
         if (mj.bucket == SLOT_EMPTY) continue;
-        if (mj.bucket != m.bucket || mj.is_start) break;
-        XYZZ q = ld_xyzz(&partials[j]);
+        if (cur != SLOT_EMPTY && (mj.bucket != cur || mj.is_start)) {
+            // run `cur` ends here
+            if (cur_start) {
+                st_xyzz(&buckets[cur], acc);
+            } else {  // continues a run from an earlier thread: only possible for the first run
+                st_xyzz(&pout[2 * (size_t)t], acc);
+                m0 = PartialMeta{cur, 0};
+            }
+            flushed_any = true;
+            acc = XYZZ::inf();
+            cur = SLOT_EMPTY;
+        }
+        if (cur == SLOT_EMPTY) { cur = mj.bucket; cur_start = mj.is_start; }
+        XYZZ q = ld_xyzz(&pin[j]);
         xyzz_add(acc, q);
     }
-    st_xyzz(&buckets[m.bucket], acc);
+    if (cur != SLOT_EMPTY) {
+        if (last_thread && cur_start) {
+            st_xyzz(&buckets[cur], acc);
+        } else if (!flushed_any) {
+            st_xyzz(&pout[2 * (size_t)t], acc);
+            m0 = PartialMeta{cur, cur_start};
+        } else {
+            st_xyzz(&pout[2 * (size_t)t + 1], acc);
+            m1 = PartialMeta{cur, cur_start};
+        }
+    }
+    mout[2 * (size_t)t] = m0;
+    mout[2 * (size_t)t + 1] = m1;
 }
 
 // --------------------------------------------------------------------------
@@ -408,6 +445,8 @@ struct MsmPlan {
     uint32_t nb;        // buckets
     uint32_t chunk, nthreads, nslots;
     uint32_t red_m, red_count;
+    uint32_t fix_slots;
+    size_t off_fixp0, off_fixp1, off_fixm0, off_fixm1;
     size_t off_keys0, off_keys1, off_vals0, off_vals1, off_zero, off_buckets, off_partials, off_meta, off_red0,
         off_red1, off_result, off_cub, cub_bytes, bytes;
 };
@@ -442,6 +481,11 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.off_buckets = take((size_t)p.nb * sizeof(XYZZ));
     p.off_partials = take((size_t)p.nslots * sizeof(XYZZ));
     p.off_meta = take((size_t)p.nslots * sizeof(PartialMeta));
+    p.fix_slots = 2 * ((p.nslots + FIX_F - 1) / FIX_F) + 2;
+    p.off_fixp0 = take((size_t)p.fix_slots * sizeof(XYZZ));
+    p.off_fixp1 = take((size_t)p.fix_slots * sizeof(XYZZ));
+    p.off_fixm0 = take((size_t)p.fix_slots * sizeof(PartialMeta));
+    p.off_fixm1 = take((size_t)p.fix_slots * sizeof(PartialMeta));
     p.off_red0 = take((size_t)p.red_count * sizeof(XYZZ));
     p.off_red1 = take((size_t)(p.red_count / 64 + 2) * sizeof(XYZZ));
     p.off_result = take(sizeof(XYZZ) * 2);
@@ -494,20 +538,48 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
 
     KZG_CUDA(cudaMemsetAsync(zero, 0, 8, stream));
     KZG_CUDA(cudaMemsetAsync(buckets, 0, (size_t)p.nb * sizeof(XYZZ), stream));
+    stage_begin(ST_MSM_DIGITS, stream);
     msm_digits_kernel<<<div_up(m, 256), 256, 0, stream>>>((const Fr*)d_scalars, (uint32_t)m, (uint32_t)s->n, s->c,
                                                           s->nwin, keys0, vals0, zero);
     KZG_LAUNCHED();
+    stage_end(ST_MSM_DIGITS, stream);
+    stage_begin(ST_MSM_SORT, stream);
     size_t cub_bytes = p.cub_bytes;
     KZG_CUDA(cub::DeviceRadixSort::SortPairs(w + p.off_cub, cub_bytes, keys0, keys1, vals0, vals1, p.total, 0, s->c,
                                              stream));
     ctx().launches += 4;  // CUB onesweep: histogram + scan + passes (library kernels; approximate count)
+    stage_end(ST_MSM_SORT, stream);
+    stage_begin(ST_MSM_ACCUMULATE, stream);
     msm_accumulate_kernel<<<div_up(p.nthreads, 128), 128, 0, stream>>>(keys1, vals1, s->table, p.total, zero, p.chunk,
                                                                       buckets, partials, meta, p.nthreads);
     KZG_LAUNCHED();
-    msm_fixup_kernel<<<div_up(p.nslots, 128), 128, 0, stream>>>(partials, meta, p.nslots, buckets);
-    KZG_LAUNCHED();
+    stage_end(ST_MSM_ACCUMULATE, stream);
+    stage_begin(ST_MSM_FIXUP, stream);
+    {
+        const XYZZ* pin = partials;
+        const PartialMeta* min_ = meta;
+        uint32_t nslots_in = p.nslots;
+        XYZZ* pbuf[2] = {(XYZZ*)(w + p.off_fixp0), (XYZZ*)(w + p.off_fixp1)};
+        PartialMeta* mbuf[2] = {(PartialMeta*)(w + p.off_fixm0), (PartialMeta*)(w + p.off_fixm1)};
+        int which = 0;
+        for (;;) {
+            uint32_t nth = (nslots_in + FIX_F - 1) / FIX_F;
+            msm_fixup_level_kernel<<<div_up(nth, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets, pbuf[which],
+                                                                         mbuf[which], nth);
+            KZG_LAUNCHED();
+            if (nth == 1) break;
+            pin = pbuf[which];
+            min_ = mbuf[which];
+            nslots_in = 2 * nth;
+            which ^= 1;
+        }
+    }
+    stage_end(ST_MSM_FIXUP, stream);
+    stage_begin(ST_MSM_BUCKET_REDUCE, stream);
     msm_bucket_reduce_kernel<<<div_up(p.red_count, 64), 64, 0, stream>>>(buckets, p.nb, p.red_m, red0);
     KZG_LAUNCHED();
+    stage_end(ST_MSM_BUCKET_REDUCE, stream);
+    stage_begin(ST_MSM_FINISH, stream);
     // tree sum red0[0..red_count) -> result (ping-pong red1 / red0)
     uint32_t count = p.red_count;
     XYZZ* src = red0;
@@ -530,6 +602,7 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
 int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream) {
     msm_finish_kernel<<<1, 32, 0, stream>>>(d_xyzz, d_out, mode);
     KZG_LAUNCHED();
+    stage_end(ST_MSM_FINISH, stream);
     return KZGB_OK;
 }
 
