@@ -103,6 +103,44 @@ KZGB_API int kzgb_msm_g1_dev(kzgb_srs* srs, const void* d_scalars, size_t m, voi
 /* Multi-GPU combine: sums `count` raw XYZZ partial sums (gathered from the ranks) into one point. */
 KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream);
 
+/* ---- Fr NTT: replaces the bodies of EvaluationDomain::fft (ft.rs:111-113) and ifft (ft.rs:115-140),
+ * i.e. best_fft/serial_fft/parallel_fft (ft.rs:274-387).  In place over 2^log_n Montgomery-form elements,
+ * natural order in and out; out[k] = sum_j a[j]*omega^(jk) with omega = root_of_unity^(2^(32-log_n))
+ * (ft.rs:73); inverse uses omega^-1 and multiplies by n^-1.  log_n >= 32 -> KZGB_DEGREE_TOO_LARGE (ft.rs:67). */
+KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse);
+KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* stream);
+
+/* ---- quotient by a linear factor: Polynomial::long_division with divisor X - x (polynomial.rs:193-227) as used
+ * by create_witness (coeff_form.rs:70-71).  p: n >= 1 coefficients low -> high (= slice_coeffs()); computes
+ * q = (p - y) div (X - x) (n-1 coefficients, not degree-shrunk, as polynomial.rs:202-205) and rem = p(x) - y.
+ * y may be NULL (y = 0). */
+KZGB_API int kzgb_divide_linear(const kzgb_fr* p, size_t n, const kzgb_fr* x, const kzgb_fr* y, kzgb_fr* q_out,
+                                kzgb_fr* rem_out);
+KZGB_API int kzgb_divide_linear_dev(const void* d_p, size_t n, const void* d_xy, int use_y, void* d_q, void* d_rem,
+                                    void* stream);
+
+/* ---- KZGProver::create_witness (coeff_form.rs:66-81): psi = (p - y)/(X - x), w = MSM(gs[..n-1], psi).to_affine().
+ * Returns KZGB_POINT_NOT_ON_POLYNOMIAL when the remainder is non-zero (coeff_form.rs:74).  n = degree + 1. */
+KZGB_API int kzgb_witness_coeff(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* x, const kzgb_fr* y,
+                                kzgb_p1_affine* out);
+/* device variant: d_xy = {x, y}; d_work = n Fr of scratch (receives psi); d_out = 96 B; synchronises the stream. */
+KZGB_API int kzgb_witness_coeff_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xy, void* d_work,
+                                    void* d_out, void* stream);
+
+/* ---- evaluation form: div_by_omega_i(evals - evals[i], i) (eval_form.rs:58-84, 125-131) and
+ * KZGProverEvalForm::create_witness (eval_form.rs:124-140) over the Lagrange-basis SRS.  d = 2^log_d. */
+KZGB_API int kzgb_div_by_omega_i(const kzgb_fr* evals, uint32_t log_d, size_t i, kzgb_fr* q_out);
+KZGB_API int kzgb_witness_eval(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uint32_t log_d, size_t i,
+                               kzgb_p1_affine* out);
+KZGB_API int kzgb_witness_eval_dev(kzgb_srs* lagrange_srs, const void* d_evals, uint32_t log_d, size_t i, void* d_work,
+                                   void* d_out, void* stream);
+
+/* ---- stage timers (CUDA events on the launching stream; bench.py's roofline) --- */
+KZGB_API int kzgb_profile_enable(int on);
+KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts); /* arrays of kzgb_profile_stage_count() */
+KZGB_API int kzgb_profile_stage_count(void);
+KZGB_API const char* kzgb_profile_stage_name(int stage);
+
 /* ---- synthetic inputs: splitmix64 Fr stream, Montgomery form, on the device ----
  * element i of stream `seed` = 4 consecutive outputs as a 256-bit LE integer mod r (mode 0), or a single
  * u64 (mode 1, the distribution of benches/commit_coeff_form.rs:16-20). */

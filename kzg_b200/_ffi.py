@@ -229,3 +229,57 @@ def profile_read() -> dict:
     check(l.kzgb_profile_read(sums, cnts))
     l.kzgb_profile_stage_name.restype = C.c_char_p
     return {l.kzgb_profile_stage_name(i).decode(): (sums[i], int(cnts[i])) for i in range(n) if cnts[i]}
+
+
+def ntt(a, log_n: int, inverse: bool = False) -> np.ndarray:
+    """Host vector ([2^log_n,4] u64 Montgomery Fr) -> transformed copy.  Status 2 raises in the host mirror."""
+    a = u64(a, (-1, 4)).copy()
+    st = check(lib().kzgb_ntt_fr(ptr(a), C.c_uint32(log_n), C.c_int(int(inverse))))
+    return st, a
+
+
+def ntt_dev(d_inout: int, log_n: int, inverse: bool = False, stream: int = 0) -> int:
+    return check(lib().kzgb_ntt_fr_dev(C.c_void_p(d_inout), C.c_uint32(log_n), C.c_int(int(inverse)), C.c_void_p(stream)))
+
+
+def divide_linear(p, x, y=None):
+    """(q, rem) = ((p - y) div (X - x), p(x) - y) on host vectors."""
+    p = u64(p, (-1, 4))
+    n = len(p)
+    q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64)
+    rem = np.zeros(4, dtype=np.uint64)
+    yy = None if y is None else u64(y, (4,))
+    check(lib().kzgb_divide_linear(ptr(p), C.c_size_t(n), ptr(u64(x, (4,))), ptr(yy), ptr(q) if n > 1 else None, ptr(rem)))
+    return q, rem
+
+
+def witness_coeff(srs: SRS, p, x, y):
+    """(status, affine) of create_witness; status 1 = PointNotOnPolynomial."""
+    p = u64(p, (-1, 4))
+    out = np.zeros(12, dtype=np.uint64)
+    st = check(lib().kzgb_witness_coeff(srs._h, ptr(p), C.c_size_t(len(p)), ptr(u64(x, (4,))), ptr(u64(y, (4,))), ptr(out)))
+    return st, out
+
+
+def witness_coeff_dev(srs: SRS, d_p: int, n: int, d_xy: int, d_work: int, d_out: int, stream: int = 0) -> int:
+    return check(lib().kzgb_witness_coeff_dev(srs._h, C.c_void_p(d_p), C.c_size_t(n), C.c_void_p(d_xy), C.c_void_p(d_work),
+                                              C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def div_by_omega_i(evals, log_d: int, i: int) -> np.ndarray:
+    evals = u64(evals, (-1, 4))
+    out = np.zeros_like(evals)
+    check(lib().kzgb_div_by_omega_i(ptr(evals), C.c_uint32(log_d), C.c_size_t(i), ptr(out)))
+    return out
+
+
+def witness_eval(srs: SRS, evals, log_d: int, i: int) -> np.ndarray:
+    evals = u64(evals, (-1, 4))
+    out = np.zeros(12, dtype=np.uint64)
+    check(lib().kzgb_witness_eval(srs._h, ptr(evals), C.c_uint32(log_d), C.c_size_t(i), ptr(out)))
+    return out
+
+
+def witness_eval_dev(srs: SRS, d_evals: int, log_d: int, i: int, d_work: int, d_out: int, stream: int = 0) -> int:
+    return check(lib().kzgb_witness_eval_dev(srs._h, C.c_void_p(d_evals), C.c_uint32(log_d), C.c_size_t(i),
+                                             C.c_void_p(d_work), C.c_void_p(d_out), C.c_void_p(stream)))

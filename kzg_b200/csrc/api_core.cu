@@ -44,6 +44,24 @@ void* scratch_reserve(size_t bytes) {
     return c.scratch;
 }
 
+void* staging_reserve(size_t bytes) {
+    Context& c = ctx();
+    if (bytes <= c.staging_bytes) return c.staging;
+    if (c.staging) {
+        cudaStreamSynchronize(c.stream);
+        cudaFree(c.staging);
+        c.staging = nullptr;
+        c.staging_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&c.staging, bytes);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaMalloc(staging)", __FILE__, __LINE__);
+        return nullptr;
+    }
+    c.staging_bytes = bytes;
+    return c.staging;
+}
+
 void* pinned_reserve(size_t bytes) {
     Context& c = ctx();
     if (bytes <= c.pinned_bytes) return c.pinned;
@@ -161,7 +179,10 @@ int kzgb_shutdown(void) {
     if (!c.initialised) return KZGB_OK;
     cudaStreamSynchronize(c.stream);
     if (c.scratch) cudaFree(c.scratch);
+    if (c.staging) cudaFree(c.staging);
     if (c.pinned) cudaFreeHost(c.pinned);
+    c.staging = nullptr;
+    c.staging_bytes = 0;
     cudaStreamDestroy(c.stream);
     c.scratch = nullptr;
     c.scratch_bytes = 0;

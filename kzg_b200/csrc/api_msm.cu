@@ -103,7 +103,7 @@ static int msm_host(kzgb_srs* s, const kzgb_fr* scalars, size_t m, void* out, in
     if (m > s->n) { set_error("kzgb_msm_g1: %zu scalars > %zu SRS points", m, s->n); return KZGB_ERR_INVALID_ARG; }
     Context& c = ctx();
     size_t bytes = m * sizeof(kzgb_fr);
-    char* d = (char*)scratch_reserve(bytes + 256);
+    char* d = (char*)staging_reserve(bytes + 256);
     if (!d) return KZGB_ERR_CUDA;
     if (m) KZG_CUDA(cudaMemcpyAsync(d + 256, scalars, bytes, cudaMemcpyHostToDevice, c.stream));
     const XYZZ* res = nullptr;

@@ -23,12 +23,16 @@ struct Context {
     // device scratch arena (grown on demand, reused across calls)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // device staging arena: device copies of host-pointer inputs (outer level; scratch is the inner level)
+    void* staging = nullptr;
+    size_t staging_bytes = 0;
 };
 
 Context& ctx();
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
+void* staging_reserve(size_t bytes);   // device staging for host-pointer entry points
 void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr (error set)
 
 #define KZG_CUDA(expr)                                                              \

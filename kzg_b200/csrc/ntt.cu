@@ -1,0 +1,314 @@
+// ntt.cu -- radix-2 number-theoretic transform over Fr for sm_100a.
+//
+// Replaces `best_fft` / `serial_fft` / `parallel_fft` (ft.rs:274-387) as reached
+// from `EvaluationDomain::fft` (ft.rs:111-113) and `ifft` (ft.rs:115-140):
+//     out[k] = sum_j a[j] * omega^(j*k),  natural order in, natural order out,
+// and for the inverse omega^-1 followed by a multiplication by n^-1.
+//
+// Decomposition: N = R_1 * ... * R_P (P <= 3, R_j <= 2^11).  Pass j runs, for
+// every value of the other digits, an R_j-point transform over digit j of the
+// index (stride S_j = R_{j+1}*...*R_P) inside shared memory, then multiplies by
+// the inter-pass twiddle omega_N^((N/N_j) * k_j * low).  A thread block stages a
+// tile of R_j x T elements (T consecutive low indices => T*32 B contiguous
+// segments in HBM).  The last pass stages T rows of R_P contiguous elements and
+// writes with the digits reversed (k_1 fastest) so the result is in natural
+// order; its tile is T consecutive k_1, so those writes are T*32 B contiguous
+// too.  One table omega_N^i (i < N/2) per domain serves both directions
+// (omega^-e = -omega^(N/2-e)), and every stage of every pass.
+#include "common.cuh"
+#include "field.cuh"
+#include "fr_util.cuh"
+#include "ntt.cuh"
+
+namespace kzg {
+
+constexpr int NTT_THREADS = 256;
+constexpr int NTT_MAX_TILE_LOG = 11;  // 2048 elements = 64 KiB of shared memory per block
+
+struct NttPassParams {
+    uint32_t log_n;      // transform size
+    uint32_t log_r;      // this pass's radix
+    uint32_t log_t;      // tile width (columns / rows per block)
+    uint32_t log_s;      // stride of this pass's digit (non-last passes)
+    uint32_t log_nj;     // log2(R_j * S_j)
+    uint32_t log_r1;     // last pass: radix of pass 1 (0 when P == 1)
+    uint32_t log_r2;     // last pass: radix of pass 2 when P == 3, else 0
+    uint32_t npass;      // P
+    uint32_t inverse;
+};
+
+KZG_DI Fr lds_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+KZG_DI void sts_fr(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+KZG_DI Fr ldg_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+// omega_N^e (or omega_N^-e) from the half table; `neg` = the value is the negative of the returned element
+KZG_DI Fr twiddle(const Fr* __restrict__ tw, uint32_t e, uint32_t log_n, uint32_t inverse, bool& neg) {
+    const uint32_t mask = (log_n >= 32) ? 0xffffffffu : ((1u << log_n) - 1);
+    e &= mask;
+    if (inverse) e = (0u - e) & mask;
+    const uint32_t half = 1u << (log_n - 1);
+    neg = (e & half) != 0;
+    return ldg_fr(&tw[e & (half - 1)]);
+}
+
+template <bool LAST>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
+                                                               NttPassParams p, Fr minv) {
+    extern __shared__ uint4 ntt_smem_raw[];
+    Fr* sm = reinterpret_cast<Fr*>(ntt_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t R = 1u << p.log_r, T = 1u << p.log_t;
+    const uint32_t E = R * T;
+    const uint64_t tile = blockIdx.x;
+    uint64_t base = 0;      // non-last: address of (d = 0, tl = 0)
+    uint64_t low0 = 0;
+    uint64_t k10 = 0, k2 = 0;
+    if (!LAST) {
+        const uint64_t tiles_per_hi = (1ull << p.log_s) >> p.log_t;
+        const uint64_t hi = tile / tiles_per_hi;
+        low0 = (tile % tiles_per_hi) << p.log_t;
+        base = (hi << p.log_nj) + low0;
+        for (uint32_t e = tid; e < E; e += NTT_THREADS) {
+            uint32_t d = e >> p.log_t, tl = e & (T - 1);
+            uint32_t dr = __brev(d) >> (32 - p.log_r);
+            if (p.log_r == 0) dr = 0;
+            sts_fr(&sm[(dr << p.log_t) + tl], lds_fr(&in[base + ((uint64_t)d << p.log_s) + tl]));
+        }
+    } else {
+        if (p.npass > 1) {
+            const uint64_t ntile_k1 = (1ull << p.log_r1) >> p.log_t;
+            k2 = tile / ntile_k1;
+            k10 = (tile % ntile_k1) << p.log_t;
+        }
+        const uint32_t log_s1 = p.log_n - p.log_r1;  // stride of digit 1
+        for (uint32_t e = tid; e < E; e += NTT_THREADS) {
+            uint32_t t = e >> p.log_r, d = e & (R - 1);
+            uint32_t dr = p.log_r ? (__brev(d) >> (32 - p.log_r)) : 0;
+            uint64_t addr = (p.npass > 1) ? (((k10 + t) << log_s1) + (k2 << p.log_r) + d) : d;
+            sts_fr(&sm[(dr << p.log_t) + t], lds_fr(&in[addr]));
+        }
+    }
+    __syncthreads();
+    // radix-2 DIT stages over the R dimension
+    for (uint32_t s = 0; s < p.log_r; s++) {
+        const uint32_t m = 1u << s;
+        for (uint32_t b = tid; b < E / 2; b += NTT_THREADS) {
+            uint32_t tl = b & (T - 1), bb = b >> p.log_t;
+            uint32_t j = bb & (m - 1);
+            uint32_t k = (bb >> s) << (s + 1);
+            uint32_t i0 = ((k + j) << p.log_t) + tl;
+            uint32_t i1 = i0 + (m << p.log_t);
+            Fr u = lds_fr(&sm[i0]);
+            Fr t = lds_fr(&sm[i1]);
+            bool neg = false;
+            if (j != 0) {
+                Fr w = twiddle(tw, j << (p.log_n - s - 1), p.log_n, p.inverse, neg);
+                t = t * w;
+            }
+            Fr hi_ = u + t, lo_ = u - t;
+            sts_fr(&sm[i0], neg ? lo_ : hi_);
+            sts_fr(&sm[i1], neg ? hi_ : lo_);
+        }
+        __syncthreads();
+    }
+    if (!LAST) {
+        for (uint32_t e = tid; e < E; e += NTT_THREADS) {
+            uint32_t kj = e >> p.log_t, tl = e & (T - 1);
+            Fr v = lds_fr(&sm[e]);
+            uint64_t ex = ((uint64_t)kj * (low0 + tl)) << (p.log_n - p.log_nj);
+            if (ex != 0) {
+                bool neg;
+                Fr w = twiddle(tw, (uint32_t)ex, p.log_n, p.inverse, neg);
+                v = v * w;
+                if (neg) v = v.neg();
+            }
+            Fr* dst = &out[base + ((uint64_t)kj << p.log_s) + tl];
+            sts_fr(dst, v);  // 2 x 16-byte global stores
+        }
+    } else {
+        for (uint32_t e = tid; e < E; e += NTT_THREADS) {
+            uint32_t kp = e >> p.log_t, t = e & (T - 1);
+            Fr v = lds_fr(&sm[e]);
+            if (p.inverse) v = v * minv;
+            uint64_t idx = (p.npass > 1)
+                               ? ((k10 + t) + (k2 << p.log_r1) + ((uint64_t)kp << (p.log_n - p.log_r)))
+                               : kp;
+            sts_fr(&out[idx], v);
+        }
+    }
+}
+
+// tw[i] = omega^i, i < count
+__global__ void ntt_twiddle_kernel(Fr* __restrict__ out, Fr omega, size_t count) {
+    constexpr int CH = 16;
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * CH;
+    if (lo >= count) return;
+    Fr cur = omega.pow_u64(lo);
+    size_t hi = min(lo + CH, count);
+    for (size_t i = lo; i < hi; i++) {
+        out[i] = cur;
+        cur = cur * omega;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------
+static Fr* g_tw[33] = {nullptr};
+
+int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out) {
+    if (log_n == 0 || log_n >= 32) { *out = nullptr; return KZGB_OK; }
+    if (!g_tw[log_n]) {
+        size_t count = (size_t)1 << (log_n - 1);
+        Fr* t = nullptr;
+        KZG_CUDA(cudaMalloc((void**)&t, count * sizeof(Fr)));
+        FrHost w = fr_host_domain_omega(log_n);
+        Fr dw;
+        memcpy(dw.l, w.l, 32);
+        ntt_twiddle_kernel<<<div_up((count + 15) / 16, 128), 128, 0, stream>>>(t, dw, count);
+        ctx().launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { cudaFree(t); return cuda_fail(e, "twiddle kernel", __FILE__, __LINE__); }
+        g_tw[log_n] = t;
+    }
+    *out = g_tw[log_n];
+    return KZGB_OK;
+}
+
+void ntt_free_twiddles() {
+    for (int i = 0; i < 33; i++) {
+        if (g_tw[i]) cudaFree(g_tw[i]);
+        g_tw[i] = nullptr;
+    }
+}
+
+struct NttPlan {
+    int npass;
+    uint32_t log_r[3];
+};
+
+static NttPlan ntt_plan(uint32_t log_n) {
+    NttPlan pl;
+    if (log_n <= 10) {
+        pl.npass = 1; pl.log_r[0] = log_n; pl.log_r[1] = pl.log_r[2] = 0;
+    } else if (log_n <= 20) {
+        pl.npass = 2; pl.log_r[0] = (log_n + 1) / 2; pl.log_r[1] = log_n / 2; pl.log_r[2] = 0;
+    } else {
+        pl.npass = 3;
+        pl.log_r[0] = (log_n + 2) / 3; pl.log_r[1] = (log_n + 1) / 3; pl.log_r[2] = log_n / 3;
+    }
+    return pl;
+}
+
+static bool g_ntt_attr_set = false;
+
+// In-place (for the caller) transform of d_data[0 .. 2^log_n); d_tmp is a same-size scratch buffer
+// (unused when the plan has one pass).
+int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream) {
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;  // ft.rs:67-69
+    if (log_n == 0) return KZGB_OK;                  // size-1 transform is the identity (minv = 1)
+    if (!g_ntt_attr_set) {
+        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        g_ntt_attr_set = true;
+    }
+    const Fr* tw = nullptr;
+    int st = ntt_get_twiddles(log_n, stream, &tw);
+    if (st) return st;
+    NttPlan pl = ntt_plan(log_n);
+    Fr minv;
+    for (int i = 0; i < 8; i++) minv.l[i] = FrParams::one(i);
+    if (inverse) {
+        FrHost mi = fr_host_inv(fr_host_from_u64(1ull << log_n));
+        memcpy(minv.l, mi.l, 32);
+    }
+    StageScope sc(ST_NTT, stream);
+    uint32_t log_s = log_n;
+    for (int j = 0; j < pl.npass; j++) {
+        NttPassParams p;
+        p.log_n = log_n;
+        p.log_r = pl.log_r[j];
+        log_s -= p.log_r;
+        p.log_s = log_s;
+        p.log_nj = p.log_r + log_s;
+        p.log_r1 = pl.npass > 1 ? pl.log_r[0] : 0;
+        p.log_r2 = pl.npass > 2 ? pl.log_r[1] : 0;
+        p.npass = pl.npass;
+        p.inverse = inverse ? 1 : 0;
+        bool last = (j == pl.npass - 1);
+        uint32_t log_t;
+        if (!last) log_t = std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, log_s);
+        else log_t = pl.npass > 1 ? std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, p.log_r1) : 0;
+        p.log_t = log_t;
+        size_t tiles = ((size_t)1 << log_n) >> (p.log_r + log_t);
+        size_t smem = ((size_t)32 << (p.log_r + log_t));
+        const Fr* src;
+        Fr* dst;
+        if (pl.npass == 1) { src = d_data; dst = d_data; }
+        else if (j == 0) { src = d_data; dst = d_tmp; }
+        else if (last) { src = d_tmp; dst = d_data; }
+        else { src = d_tmp; dst = d_tmp; }
+        if (last) ntt_pass_kernel<true><<<(unsigned)tiles, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
+        else ntt_pass_kernel<false><<<(unsigned)tiles, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
+        KZG_LAUNCHED();
+    }
+    return KZGB_OK;
+}
+
+}  // namespace kzg
+
+using namespace kzg;
+
+extern "C" {
+
+KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* stream) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
+    if (!d_inout) { set_error("kzgb_ntt_fr_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    size_t bytes = (size_t)32 << log_n;
+    Fr* tmp = nullptr;
+    if (log_n > 10) {
+        tmp = (Fr*)scratch_reserve(bytes);
+        if (!tmp) return KZGB_ERR_CUDA;
+    }
+    return ntt_run((Fr*)d_inout, tmp, log_n, inverse != 0, st);
+}
+
+KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
+    if (!inout) { set_error("kzgb_ntt_fr: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    size_t bytes = (size_t)32 << log_n;
+    char* d = (char*)scratch_reserve(2 * bytes);
+    if (!d) return KZGB_ERR_CUDA;
+    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, c.stream));
+    int st = ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, c.stream);
+    if (st) return st;
+    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, c.stream));
+    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    return KZGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,11 @@
+// ntt.cuh -- internal NTT driver interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "field.cuh"
+
+namespace kzg {
+int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream);
+int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out);
+void ntt_free_twiddles();
+}  // namespace kzg
