@@ -127,6 +127,20 @@ KZGB_API int kzgb_witness_coeff(kzgb_srs* srs, const kzgb_fr* p, size_t n, const
 KZGB_API int kzgb_witness_coeff_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xy, void* d_work,
                                     void* d_out, void* stream);
 
+/* ---- KZGProver::create_witness_batched (coeff_form.rs:83-111):
+ *   r = Polynomial::lagrange_interpolation_with_tree(xs, ys) (polynomial.rs:237-264; tree :303-365),
+ *   psi = (p - r) div prod(X - x_i) (polynomial.rs:443-460, 193-227), w = MSM(gs, psi).to_affine().
+ * r_out receives the coefficients of r: m of them (declared degree m-1), or for m == 1 the TWO coefficients of
+ * X + (y - x) -- the reference's one-point quirk (polynomial.rs:244-247).  KZGB_POINT_NOT_ON_POLYNOMIAL when the
+ * remainder is non-zero (coeff_form.rs:96).  xs must be distinct (the reference panics; here KZGB_ERR_INVALID_ARG).
+ * 1 <= m <= 4096. */
+KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys,
+                                  size_t m, kzgb_fr* r_out, size_t* r_len, kzgb_p1_affine* w_out);
+KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xs, const void* d_ys,
+                                      size_t m, void* d_r_out, void* d_out, void* stream);
+/* interpolation alone (for tests): r_out has max(m,2) entries */
+KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kzgb_fr* r_out, size_t* r_len);
+
 /* ---- evaluation form: div_by_omega_i(evals - evals[i], i) (eval_form.rs:58-84, 125-131) and
  * KZGProverEvalForm::create_witness (eval_form.rs:124-140) over the Lagrange-basis SRS.  d = 2^log_d. */
 KZGB_API int kzgb_div_by_omega_i(const kzgb_fr* evals, uint32_t log_d, size_t i, kzgb_fr* q_out);

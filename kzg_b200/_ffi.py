@@ -283,3 +283,31 @@ def witness_eval(srs: SRS, evals, log_d: int, i: int) -> np.ndarray:
 def witness_eval_dev(srs: SRS, d_evals: int, log_d: int, i: int, d_work: int, d_out: int, stream: int = 0) -> int:
     return check(lib().kzgb_witness_eval_dev(srs._h, C.c_void_p(d_evals), C.c_uint32(log_d), C.c_size_t(i),
                                              C.c_void_p(d_work), C.c_void_p(d_out), C.c_void_p(stream)))
+
+
+def interpolate(xs, ys) -> np.ndarray:
+    xs, ys = u64(xs, (-1, 4)), u64(ys, (-1, 4))
+    m = len(xs)
+    out = np.zeros((max(m, 2), 4), dtype=np.uint64)
+    rl = C.c_size_t(0)
+    check(lib().kzgb_interpolate(ptr(xs), ptr(ys), C.c_size_t(m), ptr(out), C.byref(rl)))
+    return out[: rl.value]
+
+
+def witness_batched(srs: SRS, p, xs, ys):
+    """(status, r_coeffs, w_affine) of create_witness_batched; status 1 = PointNotOnPolynomial."""
+    p, xs, ys = u64(p, (-1, 4)), u64(xs, (-1, 4)), u64(ys, (-1, 4))
+    m = len(xs)
+    r = np.zeros((max(m, 2), 4), dtype=np.uint64)
+    w = np.zeros(12, dtype=np.uint64)
+    rl = C.c_size_t(0)
+    st = check(lib().kzgb_witness_batched(srs._h, ptr(p), C.c_size_t(len(p)), ptr(xs), ptr(ys), C.c_size_t(m), ptr(r),
+                                          C.byref(rl), ptr(w)))
+    return st, r[: rl.value], w
+
+
+def witness_batched_dev(srs: SRS, d_p: int, n: int, d_xs: int, d_ys: int, m: int, d_r: int, d_out: int,
+                        stream: int = 0) -> int:
+    return check(lib().kzgb_witness_batched_dev(srs._h, C.c_void_p(d_p), C.c_size_t(n), C.c_void_p(d_xs),
+                                                C.c_void_p(d_ys), C.c_size_t(m), C.c_void_p(d_r), C.c_void_p(d_out),
+                                                C.c_void_p(stream)))

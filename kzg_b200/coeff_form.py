@@ -1,0 +1,64 @@
+"""coeff_form.rs (prover half): KZGProver, KZGBatchWitness -- host mirror over the C ABI."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _ffi
+from .params import KZGParams, PointNotOnPolynomial
+from .polynomial import Polynomial
+
+
+class KZGBatchWitness:
+    """coeff_form.rs:14-35."""
+
+    def __init__(self, r: Polynomial, w: np.ndarray):
+        self.r = r
+        self.w = w
+
+    def elem(self) -> np.ndarray:
+        return self.w
+
+    def polynomial(self) -> Polynomial:
+        return self.r
+
+    def __eq__(self, other) -> bool:
+        return self.r == other.r and bool((self.w == other.w).all())
+
+
+class KZGProver:
+    """coeff_form.rs:38-112."""
+
+    def __init__(self, parameters: KZGParams):
+        self._parameters = parameters
+
+    def parameters(self) -> KZGParams:
+        return self._parameters
+
+    def commit(self, polynomial: Polynomial) -> np.ndarray:
+        """coeff_form.rs:59-64 -> G1Affine (uint64[12])."""
+        n = polynomial.num_coeffs()
+        if n > len(self._parameters):
+            # `&self.parameters.gs[..polynomial.num_coeffs()]` panics (coeff_form.rs:60)
+            raise IndexError(f"range end index {n} out of range for slice of length {len(self._parameters)}")
+        return self._parameters.srs.msm(polynomial.slice_coeffs())
+
+    def create_witness(self, polynomial: Polynomial, point) -> np.ndarray:
+        """coeff_form.rs:66-81.  Raises PointNotOnPolynomial when (X - x) does not divide p - y."""
+        x, y = point
+        coeffs = polynomial.slice_coeffs()
+        # degree-0 dividends never reach the device: zero -> ([0], None) -> gs[0]*0; non-zero constant ->
+        # ([0], Some(self)) -> Err (polynomial.rs:194-199).  The C ABI implements exactly the same rule.
+        st, w = _ffi.witness_coeff(self._parameters.srs, coeffs, x, y)
+        if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
+            raise PointNotOnPolynomial()
+        return w
+
+    def create_witness_batched(self, polynomial: Polynomial, xs, ys) -> KZGBatchWitness:
+        """coeff_form.rs:83-111."""
+        xs = _ffi.u64(xs, (-1, 4))
+        ys = _ffi.u64(ys, (-1, 4))
+        assert len(xs) == len(ys)  # polynomial.rs:242
+        st, r, w = _ffi.witness_batched(self._parameters.srs, polynomial.slice_coeffs(), xs, ys)
+        if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
+            raise PointNotOnPolynomial()
+        return KZGBatchWitness(Polynomial(r, len(r) - 1), w)

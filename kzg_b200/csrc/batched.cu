@@ -1,0 +1,444 @@
+// batched.cu -- the batched-opening quotient of `KZGProver::create_witness_batched`
+// (coeff_form.rs:83-111):
+//     r   = interpolation through (x_i, y_i)                 (polynomial.rs:237-264, 303-365)
+//     psi = (p - r) div Z,  Z = prod (X - x_i)                (polynomial.rs:443-460, 193-227)
+//     Err(PointNotOnPolynomial) iff the remainder is non-zero (coeff_form.rs:96)
+//
+// Both results are unique polynomials, so they are computed by algebraically
+// different, parallel formulations and compared bit-for-bit with the reference
+// restatement in the tests:
+//  * r_k = sum_{l>k} Z_l * P_{l-k-1},  P_e = sum_i c_i x_i^e,  c_i = y_i / Z'(x_i)
+//    (O(m^2) work in three fully parallel steps instead of the reference's
+//    recursive subproduct tree);
+//  * psi by exact division on a coset: psi~ = iNTT( NTT(A.s^j) / NTT(Z.s^j) ) . s^-j with
+//    A = p - r, N = 2^k >= len(A).  psi~ Z = A mod (X^N - s^N) and deg psi~ < N, hence
+//    Z | A  <=>  the top m coefficients of psi~ vanish -- a deterministic test that
+//    replaces the reference's "remainder is the zero polynomial".  The shift s is the
+//    first power of 7 whose N-th power differs from every x_i^N, so Z has no root
+//    on the coset.  (The reference's schoolbook loop costs (n-m)(m+1) sequential
+//    multiply-subtracts; this is three length-N NTTs.)
+#include "common.cuh"
+#include "field.cuh"
+#include "fr_util.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "batched.cuh"
+
+namespace kzg {
+
+KZG_DI Fr b_ld(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+KZG_DI void b_st(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// ---- K11: interpolation ------------------------------------------------------
+// Z(X) = prod (X - x_i): one block, coefficients ping-pong between two global buffers.
+__global__ void __launch_bounds__(1024) interp_product_kernel(const Fr* __restrict__ xs, uint32_t m, Fr* buf0, Fr* buf1,
+                                                              Fr* __restrict__ z_out) {
+    Fr* cur = buf0;
+    Fr* nxt = buf1;
+    for (uint32_t k = threadIdx.x; k <= m; k += blockDim.x) cur[k] = (k == 0) ? Fr::one() : Fr::zero();
+    __syncthreads();
+    for (uint32_t i = 0; i < m; i++) {
+        const Fr xi = xs[i];
+        // degree i -> i+1 :  new[k] = old[k-1] - x_i * old[k]
+        for (uint32_t k = threadIdx.x; k <= i + 1; k += blockDim.x) {
+            Fr v = (k >= 1) ? cur[k - 1] : Fr::zero();
+            if (k <= i) v = v - xi * cur[k];
+            nxt[k] = v;
+        }
+        __syncthreads();
+        Fr* t = cur; cur = nxt; nxt = t;
+    }
+    for (uint32_t k = threadIdx.x; k <= m; k += blockDim.x) z_out[k] = cur[k];
+}
+
+// c_i = y_i / prod_{j != i} (x_i - x_j);   flag |= 2 when two x coincide (the reference panics:
+// `c.invert().unwrap()`, polynomial.rs:260)
+__global__ void interp_weights_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ ys, uint32_t m,
+                                      Fr* __restrict__ c, int* __restrict__ flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Fr xi = xs[i];
+    Fr d = Fr::one();
+    for (uint32_t j = 0; j < m; j++) {
+        if (j != i) d = d * (xi - xs[j]);
+    }
+    if (d.is_zero()) atomicOr(flag, 2);
+    c[i] = ys[i] * d.inv();
+}
+
+// T[e][i] = c_i * x_i^e
+__global__ void interp_powers_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ c, uint32_t m,
+                                     Fr* __restrict__ T) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Fr xi = xs[i];
+    Fr v = c[i];
+    for (uint32_t e = 0; e < m; e++) {
+        b_st(&T[(size_t)e * m + i], v);
+        v = v * xi;
+    }
+}
+
+// P_e = sum_i T[e][i]
+__global__ void __launch_bounds__(128) interp_powersum_kernel(const Fr* __restrict__ T, uint32_t m, Fr* __restrict__ P) {
+    __shared__ Fr sh[128];
+    const uint32_t e = blockIdx.x;
+    Fr acc = Fr::zero();
+    for (uint32_t i = threadIdx.x; i < m; i += 128) acc = acc + b_ld(&T[(size_t)e * m + i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P[e] = sh[0];
+}
+
+// r_k = sum_{l=k+1}^{m} Z_l * P_{l-k-1}
+__global__ void interp_conv_kernel(const Fr* __restrict__ Z, const Fr* __restrict__ P, uint32_t m, Fr* __restrict__ r) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    Fr acc = Fr::zero();
+    for (uint32_t l = k + 1; l <= m; l++) acc = acc + Z[l] * P[l - k - 1];
+    r[k] = acc;
+}
+
+// one-point case: r = X + (y - x)  (polynomial.rs:244-247 -- reproduced, not "fixed")
+__global__ void interp_single_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ ys, Fr* __restrict__ r,
+                                     Fr* __restrict__ Z) {
+    if (threadIdx.x || blockIdx.x) return;
+    r[0] = ys[0] - xs[0];
+    r[1] = Fr::one();
+    Z[0] = xs[0].neg();
+    Z[1] = Fr::one();
+}
+
+// ---- K10: exact division by Z on a coset ---------------------------------------
+// s = 7^k for the smallest k >= 1 with (7^k)^N not in { x_i^N };  out = {s, s^-1}
+__global__ void __launch_bounds__(256) coset_shift_kernel(const Fr* __restrict__ xs, uint32_t m, uint32_t log_n,
+                                                          Fr* __restrict__ out) {
+    __shared__ int bad;
+    Fr seven = Fr::zero();
+    seven.l[0] = 7;
+    seven = seven.to_mont();
+    Fr gN = seven;
+    for (uint32_t i = 0; i < log_n; i++) gN = gN.sqr();  // 7^N
+    Fr cand = Fr::one();
+    Fr s = Fr::one();
+    for (uint32_t k = 1; k <= m + 1; k++) {
+        cand = cand * gN;  // (7^k)^N
+        s = s * seven;
+        if (threadIdx.x == 0) bad = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+            Fr v = xs[i];
+            for (uint32_t t = 0; t < log_n; t++) v = v.sqr();
+            if (v == cand) bad = 1;
+        }
+        __syncthreads();
+        int b = bad;
+        __syncthreads();
+        if (!b) break;
+    }
+    if (threadIdx.x == 0) {
+        out[0] = s;
+        out[1] = s.inv();
+    }
+}
+
+constexpr int CS_CHUNK = 16;
+// dst[j] = (a[j] - b[j]) * s^j for j < len (a has na entries, b has nb entries; missing entries are zero),
+// and 0 for len <= j < N.
+__global__ void coset_scale_kernel(const Fr* __restrict__ a, size_t na, const Fr* __restrict__ b, size_t nb, size_t len,
+                                   size_t N, const Fr* __restrict__ shift, Fr* __restrict__ dst) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * CS_CHUNK;
+    if (lo >= N) return;
+    size_t hi = min(lo + CS_CHUNK, N);
+    const Fr s = shift[0];
+    Fr pw = (lo < len) ? s.pow_u64(lo) : Fr::zero();
+    for (size_t j = lo; j < hi; j++) {
+        Fr v = Fr::zero();
+        if (j < len) {
+            if (j < na) v = b_ld(&a[j]);
+            if (b && j < nb) v = v - b_ld(&b[j]);
+            v = v * pw;
+            pw = pw * s;
+        }
+        b_st(&dst[j], v);
+    }
+}
+
+constexpr int PD_BATCH = 32;
+// a[j] <- a[j] / z[j], inversions batched per thread
+__global__ void __launch_bounds__(128) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * PD_BATCH;
+    if (lo >= N) return;
+    int cnt = (int)min((size_t)PD_BATCH, N - lo);
+    Fr prefix[PD_BATCH];
+    Fr acc = Fr::one();
+    for (int k = 0; k < cnt; k++) {
+        prefix[k] = acc;
+        acc = acc * b_ld(&z[lo + k]);
+    }
+    Fr inv = acc.inv();
+    for (int k = cnt - 1; k >= 0; k--) {
+        Fr zi = inv * prefix[k];
+        inv = inv * b_ld(&z[lo + k]);
+        b_st(&a[lo + k], b_ld(&a[lo + k]) * zi);
+    }
+}
+
+// psi[j] = q[j] * s^-j for j < keep; flag |= 1 if any q[j] != 0 for keep <= j < N
+__global__ void coset_unscale_kernel(const Fr* __restrict__ q, size_t N, size_t keep, const Fr* __restrict__ shift,
+                                     Fr* __restrict__ psi, int* __restrict__ flag) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * CS_CHUNK;
+    if (lo >= N) return;
+    size_t hi = min(lo + CS_CHUNK, N);
+    const Fr sinv = shift[1];
+    Fr pw = (lo < keep) ? sinv.pow_u64(lo) : Fr::zero();
+    int nz = 0;
+    for (size_t j = lo; j < hi; j++) {
+        Fr v = b_ld(&q[j]);
+        if (j < keep) {
+            b_st(&psi[j], v * pw);
+            pw = pw * sinv;
+        } else if (!v.is_zero()) {
+            nz = 1;
+        }
+    }
+    if (nz) atomicOr(flag, 1);
+}
+
+// flag |= 1 if (a - b) has a non-zero coefficient among the first len
+__global__ void diff_nonzero_kernel(const Fr* __restrict__ a, size_t na, const Fr* __restrict__ b, size_t nb, size_t len,
+                                    int* __restrict__ flag) {
+    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    Fr v = Fr::zero();
+    if (j < na) v = b_ld(&a[j]);
+    if (j < nb) v = v - b_ld(&b[j]);
+    if (!v.is_zero()) atomicOr(flag, 1);
+}
+
+// ---- host drivers --------------------------------------------------------------
+static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t interp_workspace_bytes(size_t m) { return al((m * m + 6 * (m + 1)) * sizeof(Fr)) + 256; }
+
+// d_r receives max(m,2) coefficients (m == 1: the two coefficients of X + (y - x)); d_Z receives m+1.
+int interpolate_run(const Fr* d_xs, const Fr* d_ys, size_t m, Fr* d_r, Fr* d_Z, int* d_flag, void* d_ws,
+                    cudaStream_t stream) {
+    if (m == 0 || m > 4096) {
+        set_error("interpolate: number of points %zu out of range (1 .. 4096)", m);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    StageScope sc(ST_INTERP, stream);
+    if (m == 1) {
+        interp_single_kernel<<<1, 32, 0, stream>>>(d_xs, d_ys, d_r, d_Z);
+        KZG_LAUNCHED();
+        return KZGB_OK;
+    }
+    Fr* ws = (Fr*)d_ws;
+    Fr* buf0 = ws;
+    Fr* buf1 = buf0 + (m + 1);
+    Fr* c = buf1 + (m + 1);
+    Fr* P = c + (m + 1);
+    Fr* T = P + (m + 1);
+    uint32_t mm = (uint32_t)m;
+    interp_product_kernel<<<1, 1024, 0, stream>>>(d_xs, mm, buf0, buf1, d_Z);
+    KZG_LAUNCHED();
+    interp_weights_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_xs, d_ys, mm, c, d_flag);
+    KZG_LAUNCHED();
+    interp_powers_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_xs, c, mm, T);
+    KZG_LAUNCHED();
+    interp_powersum_kernel<<<mm, 128, 0, stream>>>(T, mm, P);
+    KZG_LAUNCHED();
+    interp_conv_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_Z, P, mm, d_r);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+size_t batch_div_workspace_bytes(size_t n, size_t m) {
+    size_t L = n > m ? n : m;
+    if (m == 1 && L < 2) L = 2;
+    uint32_t log_n = 0;
+    while (((size_t)1 << log_n) < L) log_n++;
+    return 3 * al(((size_t)32) << log_n) + 512;
+}
+
+// psi = (p - r) div Z.  d_p: n coefficients; d_r: lr coefficients; d_Z: m+1 coefficients (monic).
+// d_psi receives *psi_len coefficients.  d_flag |= 1 when Z does not divide p - r.
+int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr* d_Z, const Fr* d_xs, size_t m,
+                     Fr* d_psi, size_t* psi_len, int* d_flag, void* d_ws, cudaStream_t stream) {
+    StageScope sc(ST_BATCH_DIV, stream);
+    size_t L = n > lr ? n : lr;  // numerator length (Sub for &Polynomial, polynomial.rs:443-460)
+    if (L <= m) {
+        // deg(numerator) < deg Z: quotient is the zero polynomial; fine only if the numerator is zero
+        // (polynomial.rs:194-199)
+        diff_nonzero_kernel<<<div_up(L, 256), 256, 0, stream>>>(d_p, n, d_r, lr, L, d_flag);
+        KZG_LAUNCHED();
+        KZG_CUDA(cudaMemsetAsync(d_psi, 0, sizeof(Fr), stream));
+        *psi_len = 1;
+        return KZGB_OK;
+    }
+    uint32_t log_n = 0;
+    while (((size_t)1 << log_n) < L) log_n++;
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
+    size_t N = (size_t)1 << log_n;
+    char* w = (char*)d_ws;
+    size_t nb = al(N * sizeof(Fr));
+    Fr* A = (Fr*)w;
+    Fr* Zb = (Fr*)(w + nb);
+    Fr* tmp = (Fr*)(w + 2 * nb);
+    Fr* shift = (Fr*)(w + 3 * nb);
+    coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, shift);
+    KZG_LAUNCHED();
+    unsigned gsz = div_up((N + CS_CHUNK - 1) / CS_CHUNK, 128);
+    coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, A);
+    KZG_LAUNCHED();
+    coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, Zb);
+    KZG_LAUNCHED();
+    int st = ntt_run(A, tmp, log_n, false, stream);
+    if (st) return st;
+    st = ntt_run(Zb, tmp, log_n, false, stream);
+    if (st) return st;
+    pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, 128), 128, 0, stream>>>(A, Zb, N);
+    KZG_LAUNCHED();
+    st = ntt_run(A, tmp, log_n, true, stream);
+    if (st) return st;
+    size_t keep = L - m;
+    coset_unscale_kernel<<<gsz, 128, 0, stream>>>(A, N, keep, shift, d_psi, d_flag);
+    KZG_LAUNCHED();
+    *psi_len = keep;
+    return KZGB_OK;
+}
+
+}  // namespace kzg
+
+using namespace kzg;
+
+extern "C" {
+
+// Lagrange interpolation through (xs[i], ys[i]) on host vectors.  r_out: max(m,2) entries; *r_len = m, or 2 when
+// m == 1 (X + (y - x), polynomial.rs:244-247).  Distinct xs required (else KZGB_ERR_INVALID_ARG; the reference panics).
+KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kzgb_fr* r_out, size_t* r_len) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    if (!xs || !ys || !r_out || !r_len || m == 0 || m > 4096) {
+        set_error("kzgb_interpolate: bad argument (1 <= m <= 4096)");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    size_t mb = al(m * 32), rb = al((m + 2) * 32);
+    char* d = (char*)staging_reserve(2 * mb + 2 * rb + 256 + interp_workspace_bytes(m));
+    if (!d) return KZGB_ERR_CUDA;
+    Fr* d_xs = (Fr*)d;
+    Fr* d_ys = (Fr*)(d + mb);
+    Fr* d_r = (Fr*)(d + 2 * mb);
+    Fr* d_Z = (Fr*)(d + 2 * mb + rb);
+    int* d_flag = (int*)(d + 2 * mb + 2 * rb);
+    char* ws = d + 2 * mb + 2 * rb + 256;
+    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemsetAsync(d_flag, 0, 4, c.stream));
+    int st = interpolate_run(d_xs, d_ys, m, d_r, d_Z, d_flag, ws, c.stream);
+    if (st) return st;
+    size_t len = m == 1 ? 2 : m;
+    int flag = 0;
+    KZG_CUDA(cudaMemcpyAsync(r_out, d_r, len * 32, cudaMemcpyDeviceToHost, c.stream));
+    KZG_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c.stream));
+    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    if (flag & 2) { set_error("kzgb_interpolate: xs are not distinct"); return KZGB_ERR_INVALID_ARG; }
+    *r_len = len;
+    return KZGB_OK;
+}
+
+// create_witness_batched (coeff_form.rs:83-111) on device-resident inputs.
+// d_p: n coefficients; d_xs, d_ys: m each; d_r_out: max(m,2) Fr; d_out: 96 B affine.  Synchronises the stream.
+KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xs, const void* d_ys,
+                                      size_t m, void* d_r_out, void* d_out, void* stream) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    if (!srs || !d_p || !d_xs || !d_ys || !d_r_out || !d_out || n == 0 || m == 0 || m > 4096) {
+        set_error("kzgb_witness_batched_dev: bad argument (1 <= m <= 4096)");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    size_t lr = m == 1 ? 2 : m;
+    size_t L = n > lr ? n : lr;
+    size_t zb = al((m + 2) * 32), psib = al((L + 1) * 32);
+    size_t wsb = std::max(interp_workspace_bytes(m), batch_div_workspace_bytes(n, m));
+    char* d = (char*)scratch_reserve(zb + psib + 256 + wsb);
+    if (!d) return KZGB_ERR_CUDA;
+    Fr* d_Z = (Fr*)d;
+    Fr* d_psi = (Fr*)(d + zb);
+    int* d_flag = (int*)(d + zb + psib);
+    char* ws = d + zb + psib + 256;
+    KZG_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
+    int rc = interpolate_run((const Fr*)d_xs, (const Fr*)d_ys, m, (Fr*)d_r_out, d_Z, d_flag, ws, st);
+    if (rc) return rc;
+    size_t psi_len = 0;
+    rc = batch_divide_run((const Fr*)d_p, n, (const Fr*)d_r_out, lr, d_Z, (const Fr*)d_xs, m, d_psi, &psi_len, d_flag, ws,
+                          st);
+    if (rc) return rc;
+    if (psi_len > srs->n) {
+        set_error("kzgb_witness_batched: quotient has %zu coefficients but the SRS holds %zu points", psi_len, srs->n);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    const XYZZ* res = nullptr;
+    rc = msm_run(srs, d_psi, psi_len, st, &res);
+    if (rc) return rc;
+    rc = msm_finish(res, d_out, 0, st);
+    if (rc) return rc;
+    int flag = 0;
+    KZG_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    KZG_CUDA(cudaStreamSynchronize(st));
+    if (flag & 2) { set_error("kzgb_witness_batched: xs are not distinct"); return KZGB_ERR_INVALID_ARG; }
+    return (flag & 1) ? KZGB_POINT_NOT_ON_POLYNOMIAL : KZGB_OK;
+}
+
+KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys, size_t m,
+                                  kzgb_fr* r_out, size_t* r_len, kzgb_p1_affine* w_out) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    if (!srs || !p || !xs || !ys || !r_out || !r_len || !w_out || n == 0 || m == 0 || m > 4096) {
+        set_error("kzgb_witness_batched: bad argument (1 <= m <= 4096)");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    size_t pb = al(n * 32), mb = al(m * 32), rb = al((m + 2) * 32);
+    char* d = (char*)staging_reserve(pb + 2 * mb + rb + 256);
+    if (!d) return KZGB_ERR_CUDA;
+    Fr* d_p = (Fr*)d;
+    Fr* d_xs = (Fr*)(d + pb);
+    Fr* d_ys = (Fr*)(d + pb + mb);
+    Fr* d_r = (Fr*)(d + pb + 2 * mb);
+    char* d_out = d + pb + 2 * mb + rb;
+    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, c.stream));
+    int rc = kzgb_witness_batched_dev(srs, d_p, n, d_xs, d_ys, m, d_r, d_out, c.stream);
+    if (rc < 0) return rc;
+    size_t len = m == 1 ? 2 : m;
+    KZG_CUDA(cudaMemcpy(r_out, d_r, len * 32, cudaMemcpyDeviceToHost));
+    KZG_CUDA(cudaMemcpy(w_out, d_out, sizeof(kzgb_p1_affine), cudaMemcpyDeviceToHost));
+    *r_len = len;
+    return rc;
+}
+
+}  // extern "C"

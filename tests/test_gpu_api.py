@@ -1,0 +1,158 @@
+"""GPU suite: the host mirror of the reference API, written to read like the reference's own tests
+(coeff_form.rs:185-399, eval_form.rs:282-484, ft.rs:406-509).  The reference's pairing-based verifier
+(out of scope) is replaced by the closed form under the known setup secret."""
+import numpy as np
+import pytest
+
+import kzg_b200 as kzg
+from kzg_b200 import scalar
+from oracle import kzg_oracle as O
+
+pytestmark = pytest.mark.gpu
+R = O.R_MOD
+SECRET = O.fr_stream(69, 1)[0]
+
+
+def point(k):
+    """k*G as blst_p1_affine limbs via the oracle."""
+    return np.array(O.g1_affine_to_blst(O.g1_to_affine(O.g1_mul(O.G1_GENERATOR, k % R))), dtype=np.uint64)
+
+
+def ev(p_ints, x):
+    return O.Polynomial.new(p_ints).eval(x)
+
+
+@pytest.fixture(scope="module")
+def params(gpu):
+    return kzg.setup(SECRET, 16)
+
+
+def test_basic(params, golden):
+    """coeff_form.rs:271-283 test_basic."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream_u64(42, 12)
+    polynomial = kzg.Polynomial.from_ints(coeffs)
+    commitment = prover.commit(polynomial)
+    assert (commitment == point(ev(coeffs, SECRET))).all()
+    other = kzg.Polynomial.from_ints(O.fr_stream_u64(43, 12))
+    assert (prover.commit(other) != commitment).any()
+    full16 = kzg.Polynomial.from_ints(O.fr_stream(42, 16))
+    assert scalar.g1_affine_compress(prover.commit(full16)).hex() == golden["coeff"][0]["commit"]
+    with pytest.raises(IndexError):                       # coeff_form.rs:60 slice panic
+        prover.commit(kzg.Polynomial.from_ints(list(range(1, 18))))
+
+
+def test_modify_single_coeff(params):
+    """coeff_form.rs:295-311."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream_u64(42, 8)
+    c = prover.commit(kzg.Polynomial.from_ints(coeffs))
+    coeffs2 = list(coeffs)
+    coeffs2[2] = (coeffs2[2] + 1) % R
+    c2 = prover.commit(kzg.Polynomial.from_ints(coeffs2))
+    assert (c2 == point(ev(coeffs, SECRET) + SECRET ** 2)).all() and (c != c2).any()
+
+
+def test_padded_polynomial_uses_declared_degree(params):
+    """coeff_form.rs:208-219: trailing zero padding then shrink_degree; only coeffs[..degree+1] are read."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream_u64(42, 6)
+    padded = kzg.Polynomial(scalar.fr_vec(coeffs + [0] * 10), 15)
+    c_stale = prover.commit(padded)                       # stale degree: zeros are still fed to the MSM
+    padded.shrink_degree()
+    assert padded.degree == 5
+    assert (prover.commit(padded) == c_stale).all() and (c_stale == point(ev(coeffs, SECRET))).all()
+
+
+def test_eval_basic(params, golden):
+    """coeff_form.rs:313-342 test_eval_basic."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream_u64(42, 13)
+    polynomial = kzg.Polynomial.from_ints(coeffs)
+    x = O.fr_stream(7, 1)[0]
+    y = ev(coeffs, x)
+    assert scalar.fr_int(polynomial.eval(scalar.fr(x))) == y
+    w = prover.create_witness(polynomial, (scalar.fr(x), scalar.fr(y)))
+    assert (w == point((ev(coeffs, SECRET) - y) * pow(SECRET - x, -1, R))).all()
+    with pytest.raises(kzg.PointNotOnPolynomial):
+        prover.create_witness(polynomial, (scalar.fr(x), scalar.fr(y + 1)))
+    # degree-1 edge case p = X + 3 at (1, 4)  (:332-341): psi has one coefficient -> gs[0] * psi[0]
+    w = prover.create_witness(kzg.Polynomial.from_ints([3, 1]), (scalar.fr(1), scalar.fr(4)))
+    assert (w == point(1)).all()
+    # constant polynomial: zero dividend -> identity; wrong value -> error (Appendix A.2, polynomial.rs:194-199)
+    assert not prover.create_witness(kzg.Polynomial.from_ints([9]), (scalar.fr(5), scalar.fr(9))).any()
+    with pytest.raises(kzg.PointNotOnPolynomial):
+        prover.create_witness(kzg.Polynomial.from_ints([9]), (scalar.fr(5), scalar.fr(8)))
+    g = golden["coeff"][0]
+    p16 = kzg.Polynomial.from_ints(O.fr_stream(42, 16))
+    w = prover.create_witness(p16, (scalar.fr(int.from_bytes(bytes.fromhex(g["x"]), "little")),
+                                    scalar.fr(int.from_bytes(bytes.fromhex(g["y"]), "little"))))
+    assert scalar.g1_affine_compress(w).hex() == g["witness"]
+
+
+@pytest.mark.parametrize("n,m", [(15, 8), (16, 4), (9, 1), (8, 8), (3, 5)])
+def test_eval_batched(params, golden, n, m):
+    """coeff_form.rs:344-398 test_eval_batched / test_eval_batched_all_points (#points == #coeffs, and more)."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream(42, n)
+    polynomial = kzg.Polynomial.from_ints(coeffs)
+    xs = O.fr_stream(7, m)
+    ys = [ev(coeffs, x) for x in xs]
+    bw = prover.create_witness_batched(polynomial, scalar.fr_vec(xs), scalar.fr_vec(ys))
+    tree = O.SubProductTree.new_from_points(xs)
+    ref_r = O.Polynomial.lagrange_interpolation_with_tree(xs, ys, tree)
+    assert bw.polynomial().degree == ref_r.degree
+    assert scalar.fr_vec_int(bw.polynomial().slice_coeffs()) == ref_r.coeffs[: ref_r.degree + 1]
+    z = 1
+    for x in xs:
+        z = z * (SECRET - x) % R
+    assert (bw.elem() == point((ev(coeffs, SECRET) - ref_r.eval(SECRET)) * pow(z, -1, R))).all()
+    ys_bad = list(ys)
+    ys_bad[-1] = (ys_bad[-1] + 1) % R
+    with pytest.raises(kzg.PointNotOnPolynomial):
+        prover.create_witness_batched(polynomial, scalar.fr_vec(xs), scalar.fr_vec(ys_bad))
+    if (n, m) == (16, 4):
+        g = golden["coeff"][0]["batched"]
+        assert scalar.g1_affine_compress(bw.elem()).hex() == g["w"]
+        assert [scalar.fr_to_bytes_le(c).hex() for c in bw.polynomial().slice_coeffs()] == g["r"]
+
+
+def test_fft_composition():
+    """ft.rs:447-479: ifft(fft(x)) == x for sizes 2^0..2^9, plus fft vs the naive DFT."""
+    for lg in range(0, 10):
+        v = O.fr_stream(5, 1 << lg)
+        dom = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(v))
+        dom.fft()
+        if lg <= 6:
+            assert scalar.fr_vec_int(dom.coeffs) == O.naive_dft(v, dom.omega)
+        dom.ifft()
+        assert scalar.fr_vec_int(dom.coeffs) == v
+
+
+def test_eval_form_prover(golden):
+    """eval_form.rs:386-483: commit / create_witness over the Lagrange basis; :318-339 div_by_omega_i."""
+    d = 16
+    params = kzg.setup(SECRET, d)
+    lagrange = kzg.compute_lagrange_basis_known_secret(SECRET, d)
+    prover = kzg.KZGProverEvalForm(params, lagrange)
+    assert prover.degree() == 16 and prover.omega() == O.compute_omega(16)[2]
+    values = O.fr_stream(42, d)
+    evals = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values))
+    commitment = prover.commit(evals)
+    coeffs = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values))
+    coeffs.ifft()
+    mono = kzg.KZGProver(params).commit(coeffs.into_polynomial())     # verify_poly path, eval_form.rs:162-171
+    assert (commitment == mono).all()
+    g = golden["eval"][0]
+    assert scalar.g1_affine_compress(commitment).hex() == g["commit"]
+    w = prover.create_witness(evals, 3)
+    assert scalar.g1_affine_compress(w).hex() == g["witness"]
+    # test_div_by_omega_i: ifft(div_by_omega_i(evals - y, 3)) == long_division(p - y, X - w^3)
+    q = kzg.div_by_omega_i(evals, 3)
+    q.ifft()
+    p = coeffs.into_polynomial().sub_constant(evals.coeffs[3])
+    quot, rem = p.long_division_linear(scalar.fr(pow(evals.omega, 3, R)))
+    assert rem is None and q.into_polynomial() == quot
+    assert not prover.create_witness_all().any()
+    with pytest.raises(AssertionError):                               # eval_form.rs:115
+        prover.commit(kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values[:8])))
