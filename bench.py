@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the KZG prover hot path on B200 (contract: see DESIGN.md "Measurement").
+
+metric : BLS12-381 G1 MSM points/sec (commit, n=2^20)   [BASELINE.json]; Fr NTT 2^22 ms is reported in `extra`.
+step   : one KZGProver::commit of a degree-(2^20 - 1) polynomial = one G1 MSM over 2^20 SRS points per GPU.
+value  : points/s with scalars and SRS resident in HBM (CUDA events on the launching stream, max over ranks).
+e2e    : the same through the C ABI's host-pointer call kzgb_msm_g1 (pinned host scalars in, affine point out).
+N > 1  : weak scaling -- every rank holds its own 2^20-point shard of an N*2^20-point SRS, partial sums are
+         all-gathered (192 B per rank) over NCCL and combined on every rank.
+--impl reference : the reference's CPU path (C restatement in oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = 20
+N_POINTS = 1 << LOG_N
+IMAD_PER_POINT_ACC = 16 * 3000          # SURVEY 8d at the canonical c=16: W=16 mixed adds of 3000 IMAD each
+IMAD_PER_POINT_MSM = 52201              # whole MSM at n=2^20, c=16
+NTT_LOG = 22
+NTT_ALGO_BYTES = 2 * 2 * 32 * (1 << NTT_LOG)   # 2 passes x (read+write) x 32 B x N
+CPU_SAMPLE_LOG = 18   # cpu_baseline leg of the GPU run: one MSM over the first 2^18 points of the workload
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_run(steps, warmup, sample_log, gs_jac=None, scalars=None):
+    """Times the CPU restatement of multi_exp (oracle/kzg_cpu.c kzgo_msm_g1, all host threads) on a
+    2^sample_log-point sample of the workload.  Returns (points_per_s, cores, ms_per_step)."""
+    from oracle import cpu
+    cores = os.cpu_count() or 1
+    m = 1 << sample_log
+    if gs_jac is None:
+        # no GPU needed: SRS sample from the oracle's own generator (gs[i] = s^i G), built with all threads
+        s = cpu.fr_stream(69, 1)[0]
+        sc = cpu.fr_stream(1000, m)                       # any m scalars -> sc[i]*G points (same cost profile)
+        import numpy as np
+        G = cpu.g1_generator()
+        base = cpu.setup_g1(s, 256)
+        gs_jac = np.tile(base, (m // 256, 1))[:m].copy()  # repeated real curve points; MSM cost does not depend on them
+    if scalars is None:
+        scalars = cpu.fr_stream(42, m)
+    for _ in range(max(0, min(warmup, 1))):
+        cpu.msm_g1(gs_jac[: 1 << 12], scalars[: 1 << 12], cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu.msm_g1(gs_jac, scalars, cores)
+    dt = (time.perf_counter() - t0) / steps
+    return m / dt, cores, dt * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    # size the per-step sample so that K steps take about 100 s of wall clock: calibrate on 2^14 points
+    cal_pps, _, _ = cpu_reference_run(1, 1, 14)
+    budget_points = cal_pps * 100.0 / steps
+    sample_log = 14
+    while sample_log < LOG_N and (1 << (sample_log + 1)) <= budget_points:
+        sample_log += 1
+    global CPU_SAMPLE_LOG
+    CPU_SAMPLE_LOG = sample_log
+    pps, cores, ms = cpu_reference_run(steps, args.warmup, CPU_SAMPLE_LOG)
+    line = {
+        "impl": "reference", "metric": "BLS12-381 G1 MSM points/sec (commit, n=2^20)", "value": pps, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Fq 381-bit / Fr 255-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "C2 commit: G1 MSM, CPU restatement of multi_exp on a 2^%d-point sample of the n=2^20 workload" % CPU_SAMPLE_LOG},
+        "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": "MSM of 2^%d points (bucket method, threads over windows/ranges), %d step(s); portable C, not blst assembly" % (CPU_SAMPLE_LOG, steps)},
+        "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kzg_b200 import _ffi, distributed as kd, scalar
+
+    rank, world, local = kd.init_process_group_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _ffi.init(local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: per-rank shard [rank*2^20, (rank+1)*2^20) of a (world * 2^20)-point SRS ----
+    from oracle import cpu as ocpu  # used ONLY for the seeded secret, the parity check and the cpu_baseline leg
+    secret = ocpu.fr_stream(69, 1)[0]
+    total_points = world * N_POINTS
+    srs = _ffi.srs_generate(0, secret, total_points, first=rank * N_POINTS, count=N_POINTS)
+    NBUF = 8  # 8 distinct 32 MiB polynomials (256 MiB > 126 MB L2) rotated between steps
+    polys = []
+    for b in range(NBUF):
+        t = torch.empty((N_POINTS, 4), dtype=torch.int64, device=dev)
+        _ffi.fr_stream_dev(t.data_ptr(), 42 + b, N_POINTS, start=rank * N_POINTS, stream=stream)
+        polys.append(t)
+    ops = kd.CudaOps()
+
+    def step(i):
+        return kd.sharded_msm(srs, polys[i % NBUF], ops)
+
+    # ---- parity gate: result of step 0 == p(s)*G (closed form, oracle), compared as compressed G1 ----
+    out0 = step(0)
+    torch.cuda.synchronize()
+    if rank == 0 and world == 1:
+        coeffs = polys[0].cpu().numpy().view(np.uint64)
+        expect = ocpu.g1_to_affine(ocpu.g1_mul(ocpu.g1_generator(), ocpu.poly_eval(coeffs, secret)))[0]
+        got = out0.cpu().numpy().view(np.uint64)
+        if scalar.g1_affine_compress(got) != ocpu.g1_affine_compress(expect):
+            print(json.dumps({"error": "parity check failed: commit != p(s)*G"}), flush=True)
+            sys.exit(1)
+
+    # ---- on-box peak for the roofline denominator: dense IMAD.WIDE chains ----
+    imad_peak = max(_ffi.microbench(3, 8, 256, 64)["ops_per_s"] for _ in range(3))
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = _ffi.launch_count()
+    _ffi.profile_enable(True)
+    _ffi.profile_read()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    prof = _ffi.profile_read()
+    _ffi.profile_enable(False)
+    launches = _ffi.launch_count() - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = total_points / (ms_step * 1e-3)
+
+    # ---- e2e: host-pointer C-ABI call, pinned host scalars, copies inside the timed region ----
+    host_polys = [polys[b].cpu().pin_memory() for b in range(2)]
+    out_host = np.zeros(12, dtype=np.uint64)
+    import ctypes as C
+    lib = _ffi.lib()
+
+    def e2e_step(i):
+        hp = host_polys[i % 2]
+        if world == 1:
+            _ffi.check(lib.kzgb_msm_g1(srs._h, C.c_void_p(hp.data_ptr()), C.c_size_t(N_POINTS), _ffi.ptr(out_host)))
+        else:
+            d = hp.to(dev, non_blocking=True)
+            o = kd.sharded_msm(srs, d, ops)
+            o.cpu()
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    if rank != 0:
+        return
+    stage_ms = {k: v[0] / v[1] for k, v in prof.items()}
+    acc_ms = stage_ms.get("msm_accumulate")
+    extra = {"stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "window_bits": srs.window_bits,
+             "srs_table_bytes": srs.device_bytes}
+    roofline = None
+    if acc_ms:
+        achieved = IMAD_PER_POINT_ACC * N_POINTS / (acc_ms * 1e-3)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_msm_accumulate_summary.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roofline = {"bound": "int32_imad", "kernel": "msm_accumulate_kernel", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
+                    "unit": "TIMAD/s (32x32->64 multiply-adds)", "frac": achieved / imad_peak, "traffic": traffic,
+                    "peak_source": "measured live: kzgb_microbench mode 3 (dense independent IMAD.WIDE.U32 chains)",
+                    "algorithmic_work": "16 windows x 3000 IMAD per point (SURVEY 8d, canonical c=16) x 2^20 points per launch",
+                    "share_of_step": acc_ms / ms_step}
+        extra["msm_whole_frac_of_imad_peak"] = IMAD_PER_POINT_MSM * N_POINTS / (ms_step * 1e-3) / imad_peak if world == 1 else None
+
+    # ---- secondary headline: Fr NTT 2^22 (single GPU) and the C2 witness ----
+    if world == 1:
+        peaks = measured_peaks()
+        hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+        nbuf = torch.empty((1 << NTT_LOG, 4), dtype=torch.int64, device=dev)
+        _ffi.fr_stream_dev(nbuf.data_ptr(), 5, 1 << NTT_LOG, stream=stream)
+        for _ in range(3):
+            _ffi.ntt_dev(nbuf.data_ptr(), NTT_LOG, False, stream)
+        torch.cuda.synchronize()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(10):
+            _ffi.ntt_dev(nbuf.data_ptr(), NTT_LOG, False, stream)
+        n1.record()
+        torch.cuda.synchronize()
+        ntt_ms = n0.elapsed_time(n1) / 10
+        extra["ntt_2p22_ms"] = ntt_ms
+        extra["roofline_ntt"] = {"bound": "hbm", "achieved": NTT_ALGO_BYTES / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": NTT_ALGO_BYTES / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                                 "note": "the NTT is bound by Fr-multiply (IMAD) throughput, not HBM: see DESIGN.md"}
+        del nbuf
+        # C2 witness: scan + MSM(2^20 - 1), device resident
+        xy = torch.from_numpy(np.vstack([ocpu.fr_stream(7, 1)[0], np.zeros(4, dtype=np.uint64)]).view(np.int64)).to(dev)
+        work = torch.empty((N_POINTS, 4), dtype=torch.int64, device=dev)
+        rem = torch.zeros(4, dtype=torch.int64, device=dev)
+        lib.kzgb_divide_linear_dev(C.c_void_p(polys[0].data_ptr()), C.c_size_t(N_POINTS), C.c_void_p(xy.data_ptr()), C.c_int(0),
+                                   C.c_void_p(work.data_ptr()), C.c_void_p(rem.data_ptr()), C.c_void_p(stream))
+        torch.cuda.synchronize()
+        xy[1] = rem  # y = p(x)
+        wout = torch.zeros(12, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            _ffi.witness_coeff_dev(srs, polys[0].data_ptr(), N_POINTS, xy.data_ptr(), work.data_ptr(), wout.data_ptr(), stream)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            st = _ffi.witness_coeff_dev(srs, polys[0].data_ptr(), N_POINTS, xy.data_ptr(), work.data_ptr(), wout.data_ptr(), stream)
+        extra["witness_2p20_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+        extra["witness_status"] = st
+
+    cpu_baseline = None
+    if world == 1:
+        m = 1 << CPU_SAMPLE_LOG
+        aff = srs.read_affine(0, m)
+        gs = np.zeros((m, 18), dtype=np.uint64)
+        gs[:, :12] = aff
+        gs[:, 12:] = np.array([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745,
+                               0x5c071a97a256ec6d, 0x15f65ec3fa80e493], dtype=np.uint64)  # Montgomery one
+        sc = polys[0][:m].cpu().numpy().view(np.uint64)
+        pps, cores, cms = cpu_reference_run(1, 1, CPU_SAMPLE_LOG, gs, sc)
+        cpu_baseline = {"value": pps, "unit": "points/s", "cores": cores, "kind": "port",
+                        "sample": "MSM over the first 2^%d points/scalars of the same workload, 1 run, all host threads; C restatement of multi_exp (not blst assembly)" % CPU_SAMPLE_LOG,
+                        "ms": cms}
+
+    line = {
+        "metric": "BLS12-381 G1 MSM points/sec (commit, n=2^20)", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (Fq 381-bit / Fr 255-bit Montgomery, integer)", "data": "synthetic",
+        "config": {"workload": "C2 coeff-form commit: G1 MSM of a degree-(2^20-1) polynomial against a 2^20-point SRS per GPU",
+                   "points_per_gpu": N_POINTS, "scalars": "full-width uniform Fr (splitmix64 seeds 42..49)", "srs": "s^i*G, secret seed 69",
+                   "parallelism": "points sharded over %d GPU(s), all-gather of 192 B partials" % world,
+                   "cache": "8 rotating 32 MiB scalar vectors (256 MiB) + 1.9 GB point table: inputs larger than L2"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": total_points / e2e_s, "unit": "points/s", "h2d_bytes_per_step": N_POINTS * 32, "d2h_bytes_per_step": 96,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": launches, "clocks": clk.summary(), "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kzg_b200", choices=["kzg_b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,12 +21,16 @@
  *  <0  invalid argument / CUDA failure; kzgb_last_error_message() has the text.
  *      The Rust shim maps these to panic!, as the reference panics on
  *      out-of-range slices and failed asserts (coeff_form.rs:60, eval_form.rs:115).
- * Host-pointer entry points copy in/out through the library's pinned staging
- * buffers.  `_dev` entry points take device pointers (same layouts) and run on
- * the caller-supplied CUDA stream (a cudaStream_t passed as void*; NULL = the
- * library's own stream).  One process drives one GPU (kzgb_init(device)).
- * Calls are serialised per process by an internal mutex (the reference's
- * provers are Send + Sync; concurrent callers are safe, not parallel).
+ * Host-pointer entry points copy in/out on the library's own stream and return
+ * when the result is in the caller's buffer (pass pinned memory for full PCIe
+ * speed).  `_dev` entry points take device pointers (same layouts) and enqueue
+ * on the caller-supplied CUDA stream (a cudaStream_t passed as void*; NULL =
+ * the CUDA default stream) without synchronising, except where a status must
+ * be read back (the witness calls).  Scratch arenas are shared between calls:
+ * when consecutive calls use different streams the earlier stream is drained
+ * first.  One process drives one GPU (kzgb_init(device)).  Calls are
+ * serialised per process by an internal mutex (the reference's provers are
+ * Send + Sync; concurrent callers are safe, not parallel).
  */
 #ifndef KZG_B200_H
 #define KZG_B200_H

@@ -25,11 +25,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     return KZGB_ERR_CUDA;
 }
 
+cudaStream_t use_stream(cudaStream_t s) {
+    Context& c = ctx();
+    if (c.have_last && c.last_stream != s) cudaStreamSynchronize(c.last_stream);
+    c.last_stream = s;
+    c.have_last = true;
+    return s;
+}
+
 void* scratch_reserve(size_t bytes) {
     Context& c = ctx();
     if (bytes <= c.scratch_bytes) return c.scratch;
     if (c.scratch) {
-        cudaStreamSynchronize(c.stream);
+        cudaDeviceSynchronize();
         cudaFree(c.scratch);
         c.scratch = nullptr;
         c.scratch_bytes = 0;
@@ -48,7 +56,7 @@ void* staging_reserve(size_t bytes) {
     Context& c = ctx();
     if (bytes <= c.staging_bytes) return c.staging;
     if (c.staging) {
-        cudaStreamSynchronize(c.stream);
+        cudaDeviceSynchronize();
         cudaFree(c.staging);
         c.staging = nullptr;
         c.staging_bytes = 0;
@@ -190,6 +198,7 @@ int kzgb_shutdown(void) {
     c.pinned_bytes = 0;
     c.stream = nullptr;
     c.initialised = false;
+    c.have_last = false;
     return KZGB_OK;
 }
 

@@ -7,13 +7,14 @@ using namespace kzg;
 
 #define KZG_LOCK() std::lock_guard<std::recursive_mutex> _g(ctx().mu)
 
-static cudaStream_t pick_stream(void* stream) { return stream ? (cudaStream_t)stream : ctx().stream; }
+static cudaStream_t pick_stream(void* stream) { return use_stream((cudaStream_t)stream); }
 
 extern "C" {
 
 KZGB_API int kzgb_srs_create_g1(const kzgb_p1* points, size_t n, int window_bits, kzgb_srs** out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!points || !out) { set_error("kzgb_srs_create_g1: null argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_srs* s = nullptr;
     int st = srs_alloc(&s, n, window_bits);
@@ -41,6 +42,7 @@ KZGB_API int kzgb_srs_create_g1_affine(const kzgb_p1_affine* points, size_t n, i
                                        kzgb_srs** out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!points || !out) { set_error("kzgb_srs_create_g1_affine: null argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_srs* s = nullptr;
     int st = srs_alloc(&s, n, window_bits);
@@ -59,7 +61,8 @@ KZGB_API int kzgb_srs_create_g1_affine(const kzgb_p1_affine* points, size_t n, i
 KZGB_API int kzgb_srs_destroy(kzgb_srs* s) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
-    cudaStreamSynchronize(ctx().stream);
+    use_stream(ctx().stream);
+    cudaDeviceSynchronize();
     srs_free(s);
     return KZGB_OK;
 }
@@ -74,6 +77,7 @@ KZGB_API const void* kzgb_srs_device_points(const kzgb_srs* s) { return s ? s->t
 KZGB_API int kzgb_srs_read_affine(const kzgb_srs* s, size_t start, size_t count, kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!s || !out || start + count > s->n) { set_error("kzgb_srs_read_affine: bad range"); return KZGB_ERR_INVALID_ARG; }
     KZG_CUDA(cudaStreamSynchronize(ctx().stream));
     KZG_CUDA(cudaMemcpy(out, (const kzgb_p1_affine*)s->table + start, count * sizeof(kzgb_p1_affine),
@@ -99,6 +103,7 @@ KZGB_API int kzgb_msm_g1_dev(kzgb_srs* s, const void* d_scalars, size_t m, void*
 static int msm_host(kzgb_srs* s, const kzgb_fr* scalars, size_t m, void* out, int mode, size_t out_bytes) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!s || (!scalars && m) || !out) { set_error("kzgb_msm_g1: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (m > s->n) { set_error("kzgb_msm_g1: %zu scalars > %zu SRS points", m, s->n); return KZGB_ERR_INVALID_ARG; }
     Context& c = ctx();

@@ -21,6 +21,7 @@ KZGB_API int kzgb_divide_linear(const kzgb_fr* p, size_t n, const kzgb_fr* x, co
                                 kzgb_fr* rem_out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!p || !x || n == 0 || (!q_out && n > 1) || !rem_out) {
         set_error("kzgb_divide_linear: bad argument");
         return KZGB_ERR_INVALID_ARG;
@@ -55,7 +56,7 @@ KZGB_API int kzgb_divide_linear_dev(const void* d_p, size_t n, const void* d_xy,
         set_error("kzgb_divide_linear_dev: bad argument");
         return KZGB_ERR_INVALID_ARG;
     }
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     char* ws = (char*)scratch_reserve(al256(scan_workspace_bytes(n)));
     if (!ws) return KZGB_ERR_CUDA;
     const Fr* xy = (const Fr*)d_xy;
@@ -76,7 +77,7 @@ KZGB_API int kzgb_witness_coeff_dev(kzgb_srs* srs, const void* d_p, size_t n, co
         set_error("kzgb_witness_coeff_dev: quotient has %zu coefficients but the SRS holds %zu points", n - 1, srs->n);
         return KZGB_ERR_INVALID_ARG;
     }
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     size_t wsb = al256(scan_workspace_bytes(n));
     char* ws = (char*)scratch_reserve(wsb + 512);
     if (!ws) return KZGB_ERR_CUDA;
@@ -105,6 +106,7 @@ KZGB_API int kzgb_witness_coeff(kzgb_srs* srs, const kzgb_fr* p, size_t n, const
                                 kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (!srs || !p || !x || !y || !out || n == 0) {
         set_error("kzgb_witness_coeff: bad argument");
         return KZGB_ERR_INVALID_ARG;
@@ -139,6 +141,7 @@ KZGB_API int kzgb_witness_coeff(kzgb_srs* srs, const kzgb_fr* p, size_t n, const
 KZGB_API int kzgb_div_by_omega_i(const kzgb_fr* evals, uint32_t log_d, size_t i, kzgb_fr* q_out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
     size_t d = (size_t)1 << log_d;
     if (!evals || !q_out || i >= d) { set_error("kzgb_div_by_omega_i: bad argument"); return KZGB_ERR_INVALID_ARG; }
@@ -166,7 +169,7 @@ KZGB_API int kzgb_witness_eval_dev(kzgb_srs* lagrange_srs, const void* d_evals, 
         set_error("kzgb_witness_eval_dev: bad argument");
         return KZGB_ERR_INVALID_ARG;
     }
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     if (log_d == 0) {
         KZG_CUDA(cudaMemsetAsync(d_work, 0, 32, st));
     } else {
@@ -185,6 +188,7 @@ KZGB_API int kzgb_witness_eval(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uin
                                kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
     KZG_LOCK();
+    use_stream(ctx().stream);
     if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
     size_t d = (size_t)1 << log_d;
     if (!lagrange_srs || !evals || !out || i >= d) { set_error("kzgb_witness_eval: bad argument"); return KZGB_ERR_INVALID_ARG; }

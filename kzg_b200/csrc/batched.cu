@@ -339,6 +339,7 @@ KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kz
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     if (!xs || !ys || !r_out || !r_len || m == 0 || m > 4096) {
         set_error("kzgb_interpolate: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;
@@ -378,7 +379,7 @@ KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, 
         set_error("kzgb_witness_batched_dev: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;
     }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     size_t lr = m == 1 ? 2 : m;
     size_t L = n > lr ? n : lr;
     size_t zb = al((m + 2) * 32), psib = al((L + 1) * 32);
@@ -417,6 +418,7 @@ KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, con
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     if (!srs || !p || !xs || !ys || !r_out || !r_len || !w_out || n == 0 || m == 0 || m > 4096) {
         set_error("kzgb_witness_batched: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;

@@ -15,6 +15,8 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;  // library-owned stream for host-pointer entry points
+    cudaStream_t last_stream = nullptr;  // stream of the previous API call (arenas are shared: see use_stream)
+    bool have_last = false;
     std::recursive_mutex mu;
     uint64_t launches = 0;
     // pinned staging (host-pointer entry points)
@@ -31,6 +33,9 @@ struct Context {
 Context& ctx();
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// Every entry point runs its work on ONE stream.  The scratch/staging arenas and per-SRS work areas are shared
+// between calls, so when consecutive calls use different streams the earlier stream is drained first.
+cudaStream_t use_stream(cudaStream_t s);
 void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
 void* staging_reserve(size_t bytes);   // device staging for host-pointer entry points
 void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr (error set)

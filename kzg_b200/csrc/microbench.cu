@@ -93,6 +93,7 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     cudaEvent_t e0, e1;
     KZG_CUDA(cudaEventCreate(&e0));
     KZG_CUDA(cudaEventCreate(&e1));

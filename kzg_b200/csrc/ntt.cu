@@ -284,7 +284,7 @@ KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* s
     std::lock_guard<std::recursive_mutex> g(c.mu);
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!d_inout) { set_error("kzgb_ntt_fr_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     size_t bytes = (size_t)32 << log_n;
     Fr* tmp = nullptr;
     if (log_n > 10) {
@@ -298,6 +298,7 @@ KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!inout) { set_error("kzgb_ntt_fr: null pointer"); return KZGB_ERR_INVALID_ARG; }
     size_t bytes = (size_t)32 << log_n;

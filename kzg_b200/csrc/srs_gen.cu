@@ -200,7 +200,7 @@ KZGB_API int kzgb_fr_stream_dev(void* d_out, uint64_t seed, uint64_t start, size
     std::lock_guard<std::recursive_mutex> g(ctx().mu);
     if (!d_out && n) { set_error("kzgb_fr_stream_dev: null output"); return KZGB_ERR_INVALID_ARG; }
     if (n == 0) return KZGB_OK;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx().stream;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
     fr_stream_kernel<<<div_up(n, 256), 256, 0, st>>>((Fr*)d_out, seed, start, n, mode);
     KZG_LAUNCHED();
     return KZGB_OK;
@@ -213,6 +213,7 @@ KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, si
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     if (!secret || !out || count == 0 || first + count > total || (kind != 0 && kind != 1)) {
         set_error("kzgb_srs_generate: bad argument");
         return KZGB_ERR_INVALID_ARG;

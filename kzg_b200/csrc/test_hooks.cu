@@ -28,6 +28,7 @@ static int fe_binop(const void* a, const void* b, void* out, size_t n, int op) {
     KZG_REQUIRE_INIT();
     Context& c = ctx();
     std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(ctx().stream);
     if (n == 0) return KZGB_OK;
     if (!a || !out || (op <= 2 && !b)) {
         set_error("test binop: null pointer");
