@@ -159,8 +159,61 @@ struct Fe {
     KZG_DI Fe neg() const { return zero() - *this; }
     KZG_DI Fe dbl() const { return *this + *this; }
 
-    // Montgomery product a*b/R mod MOD.
+    // Montgomery product a*b/R mod MOD.  With KZG_OUTLINE_FQ_MUL the 12-limb product is a real function call
+    // (one copy of the ~700-instruction body per kernel) so that large kernels stay inside the instruction cache.
     KZG_DI friend Fe operator*(const Fe& a, const Fe& b) {
+#ifdef KZG_OUTLINE_FQ_MUL
+        if constexpr (N == 12) return mul_outlined(a, b);
+#endif
+#ifdef KZG_ROLLED_FQ_MUL
+        if constexpr (N == 12) return mul_rolled(a, b);
+#endif
+        return mul_inline(a, b);
+    }
+    // One b-limb step of the interleaved product: X is the accumulator that currently plays "even", Y "odd".
+    // After the step the roles are swapped (Y even, X odd, X shifted down by two limbs).
+    KZG_DI static void mul_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+        Y[0] = add_cc(Y[0], X[1]);
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2) {
+            X[j] = madc_lo_cc(a[j + 1], bi, X[j + 2]);
+            X[j + 1] = madc_hi_cc(a[j + 1], bi, X[j + 3]);
+        }
+        X[N - 2] = madc_lo_cc(a[N - 1], bi, 0);
+        X[N - 1] = madc_hi(a[N - 1], bi, 0);
+        Y[0] = mad_lo_cc(a[0], bi, Y[0]);
+        Y[1] = madc_hi_cc(a[0], bi, Y[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            Y[j] = madc_lo_cc(a[j], bi, Y[j]);
+            Y[j + 1] = madc_hi_cc(a[j], bi, Y[j + 1]);
+        }
+        X[N - 1] = addc(X[N - 1], 0);
+        reduce_step(Y, X);
+    }
+    // Same product as mul_inline with the limb loop kept rolled (two b-limbs per trip, b rotated through
+    // registers): ~10x less code, so kernels that inline many products stay inside the instruction cache.
+    KZG_DI static Fe mul_rolled(const Fe& a, const Fe& b) {
+        uint32_t X[N], Y[N], bb[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { X[j] = 0; Y[j] = 0; bb[j] = b.l[j]; }
+#pragma unroll 1
+        for (int i = 0; i < N; i += 2) {
+            mul_step(X, Y, a.l, bb[0]);
+            mul_step(Y, X, a.l, bb[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j++) bb[j] = bb[j + 2];
+        }
+        Fe r;
+        r.l[0] = add_cc(X[1], Y[0]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(X[j + 1], Y[j]);
+        r.l[N - 1] = addc(0, Y[N - 1]);
+        r.final_sub();
+        return r;
+    }
+    __device__ __noinline__ static Fe mul_outlined(Fe a, Fe b) { return mul_inline(a, b); }
+    KZG_DI static Fe mul_inline(const Fe& a, const Fe& b) {
         uint32_t E[N], O[N];
         // ---- i = 0: plain products, no accumulation ----
         {
@@ -264,8 +317,8 @@ struct Fe {
         }
         return acc;
     }
-    // Fermat inversion a^(MOD-2); inv(0) = 0.
-    __device__ __noinline__ Fe inv() const {
+    // Fermat inversion a^(MOD-2); inv(0) = 0.  (kept as the cross-check of inv())
+    __device__ __noinline__ Fe inv_fermat() const {
         Fe acc = one();
         Fe base = *this;
 #pragma unroll 1
@@ -274,6 +327,88 @@ struct Fe {
             base = base.sqr();
         }
         return acc;
+    }
+
+    // Montgomery inverse by Kaliski's binary "almost inverse" (shifts and subtractions only, ~1.4*bits
+    // iterations) followed by two Montgomery products for the 2^k correction: about 15x fewer cycles than the
+    // Fermat chain.  Input and output in Montgomery form; inv(0) = 0.
+    __device__ __noinline__ Fe inv() const {
+        if (is_zero()) return zero();
+        uint32_t u[N], v[N], r[N], s[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = l[i]; r[i] = 0; s[i] = 0; }
+        s[0] = 1;
+        int k = 0;
+#pragma unroll 1
+        for (;;) {
+            uint32_t vz = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) vz |= v[i];
+            if (vz == 0) break;
+            if ((u[0] & 1) == 0) {
+                shr1(u); shl1(s);
+            } else if ((v[0] & 1) == 0) {
+                shr1(v); shl1(r);
+            } else {
+                uint32_t t[N];
+                t[0] = sub_cc(v[0], u[0]);
+#pragma unroll
+                for (int i = 1; i < N; i++) t[i] = subc_cc(v[i], u[i]);
+                uint32_t borrow = subc(0, 0);
+                if (borrow) {  // u > v:  u = (u - v)/2, r = r + s, s = 2s
+                    u[0] = sub_cc(0, t[0]);
+#pragma unroll
+                    for (int i = 1; i < N; i++) u[i] = subc_cc(0, t[i]);
+                    shr1(u);
+                    addn(r, s); shl1(s);
+                } else {       // v >= u: v = (v - u)/2, s = s + r, r = 2r
+#pragma unroll
+                    for (int i = 0; i < N; i++) v[i] = t[i];
+                    shr1(v);
+                    addn(s, r); shl1(r);
+                }
+            }
+            k++;
+        }
+        // r < 2*MOD holds a^-1 * 2^k up to sign: r = MOD - (r mod MOD)
+        Fe x;
+#pragma unroll
+        for (int i = 0; i < N; i++) x.l[i] = r[i];
+        x.final_sub();
+        x = zero() - x;
+        // x = (a R)^-1 2^k.  Multiply by 2^(2w-k) R with w = 32N:  mont(x, to_mont(2^e)), e = 2w - k.
+        const int w = 32 * N;
+        int e = 2 * w - k;
+        constexpr int TOPBIT = bits() - 1;  // 2^TOPBIT < MOD
+        int e0 = e < TOPBIT ? e : TOPBIT;
+        Fe c = zero();
+#pragma unroll
+        for (int i = 0; i < N; i++) c.l[i] = ((e0 >> 5) == i) ? (1u << (e0 & 31)) : 0u;
+        for (int i = e0; i < e; i++) c = c.dbl();
+        c = c.to_mont();
+        return x * c;
+    }
+    __host__ __device__ static constexpr int bits() {
+        int b = 32 * N;
+        uint32_t top = P::mod(N - 1);
+        while (!(top & 0x80000000u)) { top <<= 1; b--; }
+        return b;
+    }
+    KZG_DI static void shr1(uint32_t* a) {
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], 1);
+        a[N - 1] >>= 1;
+    }
+    KZG_DI static void shl1(uint32_t* a) {
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
+        a[0] <<= 1;
+    }
+    KZG_DI static void addn(uint32_t* a, const uint32_t* b) {
+        a[0] = add_cc(a[0], b[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) a[i] = addc_cc(a[i], b[i]);
+        a[N - 1] = addc(a[N - 1], b[N - 1]);
     }
     // limb i of MOD-2 (borrow propagated at compile time)
     __host__ __device__ static constexpr uint32_t modm2_const(int i) {

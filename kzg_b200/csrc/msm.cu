@@ -23,6 +23,14 @@
 //               K6 XYZZ -> affine / Jacobian
 #include <cub/device/device_radix_sort.cuh>
 
+#if defined(KZG_MSM_ROLLED_MUL)
+#define KZG_ROLLED_FQ_MUL 1
+#elif !defined(KZG_MSM_INLINE_MUL)
+#define KZG_OUTLINE_FQ_MUL 1
+#endif
+
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ec.cuh"
 #include "msm.cuh"
@@ -176,15 +184,18 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
 }
 
 // K4b: hierarchical segmented reduction of the chunk-boundary partial sums.
-// The slot list (2 per producing thread, in sorted-bucket order) is cut into
-// runs: a run starts at a slot with is_start and continues over following
-// slots of the same bucket (EMPTY slots are skipped).  Each thread owns FIX_F
-// consecutive slots; runs that start and end inside its range are final and go
-// to buckets[]; the (at most two) runs that cross its range boundary become
-// the next level's slots.  Every level shrinks the list FIX_F/2-fold, so a
-// bucket holding half of all points (reference-style u64 scalars) costs
-// O(log) levels instead of one thread walking thousands of partials.
-constexpr uint32_t FIX_F = 32;
+// The slot list (2 per producing thread, in sorted-bucket order) is cut into runs: a run starts at a slot with
+// is_start and continues over following slots of the same bucket (EMPTY slots are skipped).  Each thread owns
+// FIX_F consecutive slots; runs that start and end inside its range are final and go to buckets[]; the (at most
+// two) runs that cross its range boundary become the next level's slots.  Every level shrinks the list
+// FIX_F/2-fold, so a bucket holding half of all points (reference-style u64 scalars) costs O(log) levels instead
+// of one thread walking thousands of partials.
+// Producers emit two slots each (2a: continuation of the previous producer's last bucket, 2a+1: own last bucket), so
+// the natural run pairs are (2a+1, 2a+2): ranges start at odd slots ([0, F+1), [F+1, 2F+1), ...) to keep such pairs
+// inside one thread.  A bounded look-ahead past the range end decides whether the last run is finished; if it cannot
+// tell, the run is forwarded to the next level.
+constexpr uint32_t FIX_F = 16;
+constexpr uint32_t FIX_PEEK = 4;
 
 __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
                                                               const PartialMeta* __restrict__ min_, uint32_t nslots_in,
@@ -192,8 +203,8 @@ __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __rest
                                                               PartialMeta* __restrict__ mout, uint32_t nthreads) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    uint32_t lo = t * FIX_F, hi = min(lo + FIX_F, nslots_in);
-    const bool last_thread = hi >= nslots_in;
+    uint32_t lo = t ? t * FIX_F + 1 : 0;
+    uint32_t hi = min((t + 1) * FIX_F + 1, nslots_in);
     PartialMeta m0{SLOT_EMPTY, 0}, m1{SLOT_EMPTY, 0};
     XYZZ acc = XYZZ::inf();
     uint32_t cur = SLOT_EMPTY, cur_start = 0;
@@ -218,7 +229,17 @@ __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __rest
         xyzz_add(acc, q);
     }
     if (cur != SLOT_EMPTY) {
-        if (last_thread && cur_start) {
+        // does the run end at the range boundary?
+        bool ended = false, known = false;
+        for (uint32_t j = hi; j < hi + FIX_PEEK; j++) {
+            if (j >= nslots_in) { ended = true; known = true; break; }
+            PartialMeta mj = min_[j];
+            if (mj.bucket == SLOT_EMPTY) continue;
+            ended = (mj.bucket != cur) || mj.is_start;
+            known = true;
+            break;
+        }
+        if (known && ended && cur_start) {
             st_xyzz(&buckets[cur], acc);
         } else if (!flushed_any) {
             st_xyzz(&pout[2 * (size_t)t], acc);
@@ -233,43 +254,20 @@ __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __rest
 }
 
 // --------------------------------------------------------------------------
-// K5: bucket reduction  S = sum_{b=0}^{nb-1} (b+1) * B[b]
-// thread k owns buckets [k*m, (k+1)*m):  T_k = sum (b-lo+1) B[b] + lo * sum B[b]
+// K5: bucket reduction  S = sum_{b=0}^{nb-1} (b+1) * B[b], two-level.
+// Buckets form a rows x cols matrix (b = hi*cols + lo), so
+//     S = cols * sum_hi hi * R[hi]  +  sum_lo (lo+1) * C[lo],
+// with R = row sums and C = column sums.  Every step is a short chain (<= ~16 point operations per thread):
+// (1) 2*nb additions spread over (rows+cols) blocks, (2) one small scalar multiplication per row/column and a
+// block tree sum, (3) a handful of additions and log2(cols) doublings.  No thread ever walks a long run of
+// buckets -- single-thread point additions cost ~8 us each, so the serial chain length IS the latency.
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) msm_bucket_reduce_kernel(const XYZZ* __restrict__ buckets, uint32_t nb, uint32_t m,
-                                                              XYZZ* __restrict__ out) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t lo = k * m;
-    if (lo >= nb) return;
-    uint32_t hi = min(lo + m, nb);
-    XYZZ run = XYZZ::inf(), acc = XYZZ::inf();
-    for (uint32_t b = hi; b-- > lo;) {
-        XYZZ q = ld_xyzz(&buckets[b]);
-        xyzz_add(run, q);
-        xyzz_add(acc, run);
-    }
-    if (lo) {
-        XYZZ sh = xyzz_mul_small(run, lo);
-        xyzz_add(acc, sh);
-    }
-    st_xyzz(&out[k], acc);
-}
+constexpr int RC_THREADS = 64;
 
-// block-level tree sum: out[blockIdx] = sum of in[blockIdx*per_block ...]
-constexpr int SUM_THREADS = 128;
-__global__ void __launch_bounds__(SUM_THREADS) msm_sum_kernel(const XYZZ* __restrict__ in, uint32_t count,
-                                                              uint32_t per_block, XYZZ* __restrict__ out) {
-    __shared__ XYZZ sh[SUM_THREADS];
-    uint32_t base = blockIdx.x * per_block;
-    uint32_t lim = min(base + per_block, count);
-    XYZZ acc = XYZZ::inf();
-    for (uint32_t j = base + threadIdx.x; j < lim; j += SUM_THREADS) {
-        XYZZ q = ld_xyzz(&in[j]);
-        xyzz_add(acc, q);
-    }
+KZG_DI XYZZ block_tree_sum(XYZZ acc, XYZZ* sh, int nthreads) {
     sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int s = SUM_THREADS / 2; s > 0; s >>= 1) {
+    for (int s = nthreads / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
             XYZZ a = sh[threadIdx.x];
             XYZZ b = sh[threadIdx.x + s];
@@ -278,7 +276,65 @@ __global__ void __launch_bounds__(SUM_THREADS) msm_sum_kernel(const XYZZ* __rest
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) st_xyzz(&out[blockIdx.x], sh[0]);
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(RC_THREADS) msm_rowcol_sum_kernel(const XYZZ* __restrict__ buckets, uint32_t rows,
+                                                                    uint32_t cols, XYZZ* __restrict__ R,
+                                                                    XYZZ* __restrict__ C) {
+    __shared__ XYZZ sh[RC_THREADS];
+    XYZZ acc = XYZZ::inf();
+    if (blockIdx.x < rows) {
+        const uint32_t row = blockIdx.x;
+        const uint32_t per = (cols + RC_THREADS - 1) / RC_THREADS;
+        uint32_t j0 = threadIdx.x * per, j1 = min(j0 + per, cols);
+        for (uint32_t j = j0; j < j1; j++) {
+            XYZZ q = ld_xyzz(&buckets[(size_t)row * cols + j]);
+            xyzz_add(acc, q);
+        }
+        XYZZ tot = block_tree_sum(acc, sh, RC_THREADS);
+        if (threadIdx.x == 0) st_xyzz(&R[row], tot);
+    } else {
+        const uint32_t col = blockIdx.x - rows;
+        const uint32_t per = (rows + RC_THREADS - 1) / RC_THREADS;
+        uint32_t i0 = threadIdx.x * per, i1 = min(i0 + per, rows);
+        for (uint32_t i = i0; i < i1; i++) {
+            XYZZ q = ld_xyzz(&buckets[(size_t)i * cols + col]);
+            xyzz_add(acc, q);
+        }
+        XYZZ tot = block_tree_sum(acc, sh, RC_THREADS);
+        if (threadIdx.x == 0) st_xyzz(&C[col], tot);
+    }
+}
+
+// blocks [0, nbr): partial sums of hi * R[hi];  blocks [nbr, nbr+nbc): partial sums of (lo+1) * C[lo]
+constexpr int WS_THREADS = 128;
+__global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ* __restrict__ R, uint32_t rows,
+                                                                      const XYZZ* __restrict__ C, uint32_t cols,
+                                                                      uint32_t nbr, XYZZ* __restrict__ partial) {
+    __shared__ XYZZ sh[WS_THREADS];
+    XYZZ acc = XYZZ::inf();
+    if (blockIdx.x < nbr) {
+        uint32_t hi = blockIdx.x * WS_THREADS + threadIdx.x;
+        if (hi < rows && hi > 0) acc = xyzz_mul_small(ld_xyzz(&R[hi]), hi);
+    } else {
+        uint32_t lo = (blockIdx.x - nbr) * WS_THREADS + threadIdx.x;
+        if (lo < cols) acc = xyzz_mul_small(ld_xyzz(&C[lo]), lo + 1);
+    }
+    XYZZ tot = block_tree_sum(acc, sh, WS_THREADS);
+    if (threadIdx.x == 0) st_xyzz(&partial[blockIdx.x], tot);
+}
+
+// result = 2^log_cols * (sum of the first nbr partials) + (sum of the remaining nbc partials)
+__global__ void msm_reduce_final_kernel(const XYZZ* __restrict__ partial, uint32_t nbr, uint32_t nbc, uint32_t log_cols,
+                                        XYZZ* __restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ vr = XYZZ::inf(), vc = XYZZ::inf();
+    for (uint32_t i = 0; i < nbr; i++) { XYZZ q = ld_xyzz(&partial[i]); xyzz_add(vr, q); }
+    for (uint32_t i = 0; i < nbc; i++) { XYZZ q = ld_xyzz(&partial[nbr + i]); xyzz_add(vc, q); }
+    for (uint32_t i = 0; i < log_cols; i++) vr = xyzz_dbl(vr);
+    xyzz_add(vr, vc);
+    st_xyzz(out, vr);
 }
 
 // K6: result conversion.  mode 0: affine (blst_p1_affine), 1: Jacobian (blst_p1), 2: raw XYZZ
@@ -382,14 +438,14 @@ __global__ void __launch_bounds__(128) jac_to_affine_kernel(const Jacobian* __re
 // host side
 // --------------------------------------------------------------------------
 int msm_choose_window(size_t n) {
-    // cost model in Fq multiplications: n*W mixed adds (10) + 2^(c-1) buckets * (2 full adds (14) + amortised
-    // scalar-mul/tree (~14)); table memory W*n*96 B is capped at ~1/4 of HBM.
+    // cost model in Fq multiplications, calibrated on B200 at n = 2^20: n*W mixed adds (10 each) + 2^(c-1) buckets
+    // * 30 (two full adds plus the latency-bound share of fix-up/reduction); table memory W*n*96 B is capped.
     int best = 8;
     double best_cost = 1e300;
     for (int c = 6; c <= 22; c++) {
         int w = (256 + c - 1) / c;
         if (w > MSM_MAX_WINDOWS) continue;
-        double cost = (double)n * w * 10.0 + (double)(1u << (c - 1)) * 42.0;
+        double cost = (double)n * w * 10.0 + (double)(1u << (c - 1)) * 30.0;
         if ((double)n * w * 96.0 > 40e9) continue;
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
@@ -443,10 +499,9 @@ void srs_free(kzgb_srs* s) {
 struct MsmPlan {
     size_t total;       // n_scalars * nwin
     uint32_t nb;        // buckets
-    uint32_t chunk, nthreads, nslots;
-    uint32_t red_m, red_count;
-    uint32_t fix_slots;
+    uint32_t chunk, nthreads, nslots, fix_slots;
     size_t off_fixp0, off_fixp1, off_fixm0, off_fixm1;
+    uint32_t rows, cols, log_cols, nbr, nbc;
     size_t off_keys0, off_keys1, off_vals0, off_vals1, off_zero, off_buckets, off_partials, off_meta, off_red0,
         off_red1, off_result, off_cub, cub_bytes, bytes;
 };
@@ -458,6 +513,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     // threads: a whole number of waves of (SMs * 3 blocks * 128 threads)
     size_t wave = (size_t)c.sm_count * 3 * 128;
     size_t target_chunk = 48;
+    if (const char* e = getenv("KZGB_MSM_CHUNK")) target_chunk = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : target_chunk;
     size_t waves = (p.total + wave * target_chunk - 1) / (wave * target_chunk);
     if (waves < 1) waves = 1;
     size_t nthreads = waves * wave;
@@ -468,9 +524,11 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     }
     p.chunk = (uint32_t)chunk;
     p.nthreads = (uint32_t)nthreads;
-    p.nslots = 2 * p.nthreads;
-    p.red_m = p.nb >= 32 ? 32 : p.nb;
-    p.red_count = (p.nb + p.red_m - 1) / p.red_m;
+    p.log_cols = (uint32_t)(s->c - 1) / 2;
+    p.cols = 1u << p.log_cols;
+    p.rows = p.nb >> p.log_cols;
+    p.nbr = (p.rows + WS_THREADS - 1) / WS_THREADS;
+    p.nbc = (p.cols + WS_THREADS - 1) / WS_THREADS;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     p.off_keys0 = take(p.total * 4);
@@ -479,15 +537,16 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.off_vals1 = take(p.total * 4);
     p.off_zero = take(8);
     p.off_buckets = take((size_t)p.nb * sizeof(XYZZ));
+    p.nslots = 2 * p.nthreads;
     p.off_partials = take((size_t)p.nslots * sizeof(XYZZ));
     p.off_meta = take((size_t)p.nslots * sizeof(PartialMeta));
-    p.fix_slots = 2 * ((p.nslots + FIX_F - 1) / FIX_F) + 2;
+    p.fix_slots = 2 * (p.nslots / FIX_F + 1) + 2;
     p.off_fixp0 = take((size_t)p.fix_slots * sizeof(XYZZ));
     p.off_fixp1 = take((size_t)p.fix_slots * sizeof(XYZZ));
     p.off_fixm0 = take((size_t)p.fix_slots * sizeof(PartialMeta));
     p.off_fixm1 = take((size_t)p.fix_slots * sizeof(PartialMeta));
-    p.off_red0 = take((size_t)p.red_count * sizeof(XYZZ));
-    p.off_red1 = take((size_t)(p.red_count / 64 + 2) * sizeof(XYZZ));
+    p.off_red0 = take((size_t)(p.rows + p.cols) * sizeof(XYZZ));
+    p.off_red1 = take((size_t)(p.nbr + p.nbc) * sizeof(XYZZ));
     p.off_result = take(sizeof(XYZZ) * 2);
     p.cub_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, p.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -563,7 +622,7 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
         PartialMeta* mbuf[2] = {(PartialMeta*)(w + p.off_fixm0), (PartialMeta*)(w + p.off_fixm1)};
         int which = 0;
         for (;;) {
-            uint32_t nth = (nslots_in + FIX_F - 1) / FIX_F;
+            uint32_t nth = nslots_in > 1 ? (nslots_in - 1 + FIX_F - 1) / FIX_F : 1;
             msm_fixup_level_kernel<<<div_up(nth, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets, pbuf[which],
                                                                          mbuf[which], nth);
             KZG_LAUNCHED();
@@ -576,26 +635,16 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     }
     stage_end(ST_MSM_FIXUP, stream);
     stage_begin(ST_MSM_BUCKET_REDUCE, stream);
-    msm_bucket_reduce_kernel<<<div_up(p.red_count, 64), 64, 0, stream>>>(buckets, p.nb, p.red_m, red0);
+    XYZZ* Rsum = red0;
+    XYZZ* Csum = red0 + p.rows;
+    msm_rowcol_sum_kernel<<<p.rows + p.cols, RC_THREADS, 0, stream>>>(buckets, p.rows, p.cols, Rsum, Csum);
+    KZG_LAUNCHED();
+    msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsum, p.rows, Csum, p.cols, p.nbr, red1);
+    KZG_LAUNCHED();
+    msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
     KZG_LAUNCHED();
     stage_end(ST_MSM_BUCKET_REDUCE, stream);
     stage_begin(ST_MSM_FINISH, stream);
-    // tree sum red0[0..red_count) -> result (ping-pong red1 / red0)
-    uint32_t count = p.red_count;
-    XYZZ* src = red0;
-    XYZZ* bufs[2] = {red1, red0};
-    int which = 0;
-    if (count == 1) KZG_CUDA(cudaMemcpyAsync(result, src, sizeof(XYZZ), cudaMemcpyDeviceToDevice, stream));
-    while (count > 1) {
-        const uint32_t per_block = 256;
-        uint32_t blocks = div_up(count, per_block);
-        XYZZ* o = (blocks == 1) ? result : bufs[which];
-        msm_sum_kernel<<<blocks, SUM_THREADS, 0, stream>>>(src, count, per_block, o);
-        KZG_LAUNCHED();
-        count = blocks;
-        src = o;
-        which ^= 1;
-    }
     return KZGB_OK;
 }
 

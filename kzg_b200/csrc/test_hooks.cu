@@ -5,7 +5,7 @@
 
 namespace kzg {
 
-// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a), 6 sqr(a)
+// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a), 6 sqr(a), 7 inv_fermat(a)
 template <class F>
 __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b, F* __restrict__ o, size_t n, int op) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -18,6 +18,7 @@ __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b
         case 3: r = x.inv(); break;
         case 4: r = x.to_mont(); break;
         case 5: r = x.from_mont(); break;
+        case 7: r = x.inv_fermat(); break;
         default: r = x.sqr(); break;
     }
     o[i] = r;
