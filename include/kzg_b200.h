@@ -159,6 +159,21 @@ KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts); /* arrays of k
 KZGB_API int kzgb_profile_stage_count(void);
 KZGB_API const char* kzgb_profile_stage_name(int stage);
 
+/* ---- four-step building blocks of the multi-GPU NTT (N >= 2^24, one all-to-all; structural
+ * precedent: parallel_fft, ft.rs:336-387).  View the vector as N1 x N2 (index i1*N2 + i2).  Rank g holds the slab
+ * [N1][C] of columns i2 in [g*C, (g+1)*C), C = N2/G.
+ *   kzgb_ntt4_columns_dev: in place, N1-point transforms down the columns + twiddle omega_N^(k1*i2);
+ *   (all-to-all of row blocks between ranks: done by the caller, e.g. torch.distributed / NCCL)
+ *   kzgb_ntt4_unpack_dev : recv[g][r][c] -> rows[r][g*C + c];
+ *   kzgb_ntt_batch_dev   : N2-point transforms of the N1/G local rows; row r of rank h then holds
+ *                          X[(h*N1/G + r) + N1*k2], k2 = 0..N2-1. */
+KZGB_API int kzgb_ntt4_columns_dev(void* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
+                                   int inverse, void* stream);
+KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t world, uint32_t nrows, uint32_t cols,
+                                  void* stream);
+KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint32_t batch, int inverse,
+                                const kzgb_fr* scale, void* stream);
+
 /* ---- synthetic inputs: splitmix64 Fr stream, Montgomery form, on the device ----
  * element i of stream `seed` = 4 consecutive outputs as a 256-bit LE integer mod r (mode 0), or a single
  * u64 (mode 1, the distribution of benches/commit_coeff_form.rs:16-20). */

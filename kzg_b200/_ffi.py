@@ -311,3 +311,19 @@ def witness_batched_dev(srs: SRS, d_p: int, n: int, d_xs: int, d_ys: int, m: int
     return check(lib().kzgb_witness_batched_dev(srs._h, C.c_void_p(d_p), C.c_size_t(n), C.c_void_p(d_xs),
                                                 C.c_void_p(d_ys), C.c_size_t(m), C.c_void_p(d_r), C.c_void_p(d_out),
                                                 C.c_void_p(stream)))
+
+
+def ntt4_columns_dev(d_slab: int, log_n: int, log_n1: int, log_c: int, col_offset: int, inverse: bool, stream: int = 0):
+    return check(lib().kzgb_ntt4_columns_dev(C.c_void_p(d_slab), C.c_uint32(log_n), C.c_uint32(log_n1), C.c_uint32(log_c),
+                                             C.c_uint32(col_offset), C.c_int(int(inverse)), C.c_void_p(stream)))
+
+
+def ntt4_unpack_dev(d_recv: int, d_rows: int, world: int, nrows: int, cols: int, stream: int = 0):
+    return check(lib().kzgb_ntt4_unpack_dev(C.c_void_p(d_recv), C.c_void_p(d_rows), C.c_uint32(world), C.c_uint32(nrows),
+                                            C.c_uint32(cols), C.c_void_p(stream)))
+
+
+def ntt_batch_dev(d_inout: int, d_tmp: int, log_n: int, batch: int, inverse: bool, scale=None, stream: int = 0):
+    sc = None if scale is None else u64(scale, (4,))
+    return check(lib().kzgb_ntt_batch_dev(C.c_void_p(d_inout), C.c_void_p(d_tmp), C.c_uint32(log_n), C.c_uint32(batch),
+                                          C.c_int(int(inverse)), ptr(sc), C.c_void_p(stream)))

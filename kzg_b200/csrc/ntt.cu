@@ -35,6 +35,10 @@ struct NttPassParams {
     uint32_t log_r2;     // last pass: radix of pass 2 when P == 3, else 0
     uint32_t npass;      // P
     uint32_t inverse;
+    uint32_t tw_shift;   // inter-pass twiddle exponent = (k_j * (low_offset + low)) << tw_shift
+    uint32_t low_offset; // global index of this slab's first column (four-step, multi-GPU); 0 otherwise
+    uint32_t apply_scale; // last pass: multiply by `minv`
+    uint64_t batch_stride; // elements between consecutive vectors of a batch (gridDim.y vectors)
 };
 
 KZG_DI Fr lds_fr(const Fr* p) {
@@ -78,6 +82,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t;
     const uint32_t E = R * T;
     const uint64_t tile = blockIdx.x;
+    // batched transforms: blockIdx.y selects one of gridDim.y independent length-2^log_n vectors
+    in += (size_t)blockIdx.y * p.batch_stride;
+    out += (size_t)blockIdx.y * p.batch_stride;
     uint64_t base = 0;      // non-last: address of (d = 0, tl = 0)
     uint64_t low0 = 0;
     uint64_t k10 = 0, k2 = 0;
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
         for (uint32_t e = tid; e < E; e += NTT_THREADS) {
             uint32_t kj = e >> p.log_t, tl = e & (T - 1);
             Fr v = lds_fr(&sm[e]);
-            uint64_t ex = ((uint64_t)kj * (low0 + tl)) << (p.log_n - p.log_nj);
+            uint64_t ex = ((uint64_t)kj * (p.low_offset + low0 + tl)) << p.tw_shift;
             if (ex != 0) {
                 bool neg;
                 Fr w = twiddle(tw, (uint32_t)ex, p.log_n, p.inverse, neg);
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
         for (uint32_t e = tid; e < E; e += NTT_THREADS) {
             uint32_t kp = e >> p.log_t, t = e & (T - 1);
             Fr v = lds_fr(&sm[e]);
-            if (p.inverse) v = v * minv;
+            if (p.apply_scale) v = v * minv;
             uint64_t idx = (p.npass > 1)
                                ? ((k10 + t) + (k2 << p.log_r1) + ((uint64_t)kp << (p.log_n - p.log_r)))
                                : kp;
@@ -218,24 +225,76 @@ static NttPlan ntt_plan(uint32_t log_n) {
 }
 
 static bool g_ntt_attr_set = false;
-
-// In-place (for the caller) transform of d_data[0 .. 2^log_n); d_tmp is a same-size scratch buffer
-// (unused when the plan has one pass).
-int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream) {
-    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;  // ft.rs:67-69
-    if (log_n == 0) return KZGB_OK;                  // size-1 transform is the identity (minv = 1)
+static int ntt_set_attrs() {
     if (!g_ntt_attr_set) {
         KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         g_ntt_attr_set = true;
     }
+    return KZGB_OK;
+}
+
+// Four-step, step 1 (multi-GPU NTT): this rank's slab is [N1 rows][C columns] (row-major) holding
+// a[i1*N2 + col_offset + c].  In place: N1-point transforms down every column, then the twiddle
+// omega_N^(k1 * (col_offset + c)).  One shared-memory pass (N1 <= 2^11).
+int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset, bool inverse,
+                    cudaStream_t stream) {
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
+    if (log_n1 > NTT_MAX_TILE_LOG || log_n1 > log_n) {
+        set_error("ntt_columns: log_n1 = %u out of range", log_n1);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    if (log_n == 0) return KZGB_OK;
     const Fr* tw = nullptr;
     int st = ntt_get_twiddles(log_n, stream, &tw);
+    if (st) return st;
+    st = ntt_set_attrs();
+    if (st) return st;
+    StageScope sc(ST_NTT, stream);
+    NttPassParams p;
+    p.log_n = log_n;
+    p.log_r = log_n1;
+    p.log_s = log_c;
+    p.log_nj = log_n1 + log_c;
+    p.log_r1 = p.log_r2 = 0;
+    p.npass = 2;
+    p.inverse = inverse ? 1 : 0;
+    p.tw_shift = 0;
+    p.low_offset = col_offset;
+    p.apply_scale = 0;
+    p.batch_stride = 0;
+    p.log_t = std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, log_c);
+    size_t tiles = ((size_t)1 << log_c) >> p.log_t;
+    size_t smem = (size_t)32 << (p.log_r + p.log_t);
+    Fr one;
+    for (int i = 0; i < 8; i++) one.l[i] = FrParams::one(i);
+    // stage twiddles: omega_N1^(j*N1/2m) = omega_N^(j*N/2m), i.e. the same ladder the kernel uses for any pass
+    ntt_pass_kernel<false><<<dim3((unsigned)tiles, 1), NTT_THREADS, smem, stream>>>(d_slab, d_slab, tw, p, one);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+// In-place (for the caller) transform of d_data[0 .. 2^log_n); d_tmp is a same-size scratch buffer
+// (unused when the plan has one pass).
+int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream, uint32_t batch,
+            const Fr* scale) {
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;  // ft.rs:67-69
+    if (log_n == 0 && !scale) return KZGB_OK;        // size-1 transform is the identity (minv = 1)
+    if (batch == 0) return KZGB_OK;
+    if (batch > 65535) { set_error("ntt: batch %u too large", batch); return KZGB_ERR_INVALID_ARG; }
+    const Fr* tw = nullptr;
+    int st = ntt_get_twiddles(log_n, stream, &tw);
+    if (st) return st;
+    st = ntt_set_attrs();
     if (st) return st;
     NttPlan pl = ntt_plan(log_n);
     Fr minv;
     for (int i = 0; i < 8; i++) minv.l[i] = FrParams::one(i);
-    if (inverse) {
+    bool apply_scale = inverse;
+    if (scale) {
+        minv = *scale;
+        apply_scale = true;
+    } else if (inverse) {
         FrHost mi = fr_host_inv(fr_host_from_u64(1ull << log_n));
         memcpy(minv.l, mi.l, 32);
     }
@@ -252,7 +311,11 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         p.log_r2 = pl.npass > 2 ? pl.log_r[1] : 0;
         p.npass = pl.npass;
         p.inverse = inverse ? 1 : 0;
+        p.tw_shift = log_n - p.log_nj;
+        p.low_offset = 0;
+        p.batch_stride = (uint64_t)1 << log_n;
         bool last = (j == pl.npass - 1);
+        p.apply_scale = (last && apply_scale) ? 1 : 0;
         uint32_t log_t;
         if (!last) log_t = std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, log_s);
         else log_t = pl.npass > 1 ? std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, p.log_r1) : 0;
@@ -265,11 +328,26 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         else if (j == 0) { src = d_data; dst = d_tmp; }
         else if (last) { src = d_tmp; dst = d_data; }
         else { src = d_tmp; dst = d_tmp; }
-        if (last) ntt_pass_kernel<true><<<(unsigned)tiles, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
-        else ntt_pass_kernel<false><<<(unsigned)tiles, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
+        dim3 grid((unsigned)tiles, batch);
+        if (last) ntt_pass_kernel<true><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
+        else ntt_pass_kernel<false><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
         KZG_LAUNCHED();
     }
     return KZGB_OK;
+}
+
+// Four-step, after the all-to-all: recv[g][r][c] (G blocks of rows x C) -> rows[r][g*C + c]
+__global__ void ntt4_unpack_kernel(const uint4* __restrict__ recv, uint4* __restrict__ rows, uint32_t G, uint32_t nrows,
+                                   uint32_t C) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // over uint4 halves of Fr elements
+    size_t total = (size_t)G * nrows * C * 2;
+    if (idx >= total) return;
+    size_t e = idx >> 1, half = idx & 1;
+    uint32_t c = (uint32_t)(e % C);
+    size_t t = e / C;
+    uint32_t r = (uint32_t)(t % nrows);
+    uint32_t g = (uint32_t)(t / nrows);
+    rows[(((size_t)r * G + g) * C + c) * 2 + half] = recv[idx];
 }
 
 }  // namespace kzg
@@ -292,6 +370,43 @@ KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* s
         if (!tmp) return KZGB_ERR_CUDA;
     }
     return ntt_run((Fr*)d_inout, tmp, log_n, inverse != 0, st);
+}
+
+// ---- four-step building blocks for the multi-GPU NTT (N >= 2^24) ----
+KZGB_API int kzgb_ntt4_columns_dev(void* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
+                                   int inverse, void* stream) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    if (!d_slab) { set_error("kzgb_ntt4_columns_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    cudaStream_t st = use_stream((cudaStream_t)stream);
+    return ntt_columns_run((Fr*)d_slab, log_n, log_n1, log_c, col_offset, inverse != 0, st);
+}
+
+KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t world, uint32_t nrows, uint32_t cols,
+                                  void* stream) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    if (!d_recv || !d_rows) { set_error("kzgb_ntt4_unpack_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    cudaStream_t st = use_stream((cudaStream_t)stream);
+    size_t total = (size_t)world * nrows * cols * 2;
+    ntt4_unpack_kernel<<<div_up(total, 256), 256, 0, st>>>((const uint4*)d_recv, (uint4*)d_rows, world, nrows, cols);
+    KZG_LAUNCHED();
+    return KZGB_OK;
+}
+
+// `batch` independent contiguous transforms of 2^log_n elements each (rows of the four-step matrix); when
+// scale != NULL every output is multiplied by *scale (Montgomery Fr, host pointer) instead of the default
+// (1 for forward, 2^-log_n for inverse).  d_tmp: batch * 2^log_n elements of scratch (unused for log_n <= 10).
+KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint32_t batch, int inverse,
+                                const kzgb_fr* scale, void* stream) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
+    if (!d_inout || (log_n > 10 && !d_tmp)) { set_error("kzgb_ntt_batch_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    cudaStream_t st = use_stream((cudaStream_t)stream);
+    Fr sc;
+    if (scale) memcpy(sc.l, scale->l, 32);
+    return ntt_run((Fr*)d_inout, (Fr*)d_tmp, log_n, inverse != 0, st, batch, scale ? &sc : nullptr);
 }
 
 KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {

@@ -71,3 +71,75 @@ def sharded_msm(srs_shard, scalars_shard: torch.Tensor, ops=None, group=None) ->
     out = torch.zeros(12, dtype=torch.int64, device=dev)
     ops.g1_combine(gathered, world, out)
     return out
+
+
+# ---------------------------------------------------------------------------
+# Four-step NTT across GPUs (N >= 2^24; one all-to-all)
+# ---------------------------------------------------------------------------
+def four_step_shape(log_n: int, world: int, log_n1: Optional[int] = None) -> Tuple[int, int, int]:
+    """(log_n1, log_n2, log_c): the vector is an N1 x N2 matrix (index i1*N2 + i2); every rank holds C = N2/world
+    columns.  N1 <= 2^10 keeps the column transform in one shared-memory pass with 64-byte row segments."""
+    lw = world.bit_length() - 1
+    assert 1 << lw == world, "world size must be a power of two"
+    if log_n1 is None:
+        log_n1 = min(10, log_n // 2)
+    log_n1 = max(log_n1, lw)          # at least one row block per rank
+    log_n2 = log_n - log_n1
+    assert log_n2 >= lw, "transform too small for this many ranks"
+    return log_n1, log_n2, log_n2 - lw
+
+
+def four_step_scatter(vec: np.ndarray, log_n: int, world: int, log_n1: Optional[int] = None):
+    """Natural-order vector [N, 4] -> per-rank input slabs [N1, C, 4] (slab_g[i1][c] = a[i1*N2 + g*C + c])."""
+    l1, l2, lc = four_step_shape(log_n, world, log_n1)
+    m = np.ascontiguousarray(vec).reshape(1 << l1, world, 1 << lc, 4)
+    return [np.ascontiguousarray(m[:, g]) for g in range(world)]
+
+
+def four_step_gather(rows_per_rank, log_n: int, world: int, log_n1: Optional[int] = None) -> np.ndarray:
+    """Per-rank outputs [N1/G, N2, 4] (rows_h[r][k2] = X[(h*N1/G + r) + N1*k2]) -> natural-order vector."""
+    l1, l2, lc = four_step_shape(log_n, world, log_n1)
+    full = np.concatenate([np.asarray(r).reshape(-1, 1 << l2, 4) for r in rows_per_rank], axis=0)  # [k1][k2]
+    return np.ascontiguousarray(full.transpose(1, 0, 2)).reshape(1 << log_n, 4)                   # index k1 + N1*k2
+
+
+class CudaNttOps:
+    """Local steps of the four-step NTT behind the C ABI (torch CUDA tensors, int64 views of Fr)."""
+
+    def columns(self, slab: torch.Tensor, log_n, log_n1, log_c, col_offset, inverse):
+        _ffi.ntt4_columns_dev(slab.data_ptr(), log_n, log_n1, log_c, col_offset, inverse,
+                              torch.cuda.current_stream().cuda_stream)
+
+    def unpack(self, recv: torch.Tensor, world, nrows, cols) -> torch.Tensor:
+        rows = torch.empty((nrows, world * cols, 4), dtype=torch.int64, device=recv.device)
+        _ffi.ntt4_unpack_dev(recv.data_ptr(), rows.data_ptr(), world, nrows, cols, torch.cuda.current_stream().cuda_stream)
+        return rows
+
+    def rows(self, rows: torch.Tensor, log_n2, inverse, scale):
+        tmp = torch.empty_like(rows) if log_n2 > 10 else rows
+        _ffi.ntt_batch_dev(rows.data_ptr(), tmp.data_ptr(), log_n2, rows.shape[0], inverse, scale,
+                           torch.cuda.current_stream().cuda_stream)
+
+
+def ntt_four_step(slab: torch.Tensor, log_n: int, inverse: bool = False, ops=None, group=None,
+                  log_n1: Optional[int] = None) -> torch.Tensor:
+    """Distributed NTT.  `slab`: this rank's [N1, C, 4] input slab (see four_step_scatter); it is overwritten.
+    Returns this rank's [N1/G, N2, 4] block of the result (see four_step_gather).  Same values as the single-GPU
+    transform / the reference's fft, ifft (ft.rs:111-140).  One exchange: an all-to-all of N*32/G^2 bytes per pair."""
+    ops = ops or CudaNttOps()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    l1, l2, lc = four_step_shape(log_n, world, log_n1)
+    n1, c = 1 << l1, 1 << lc
+    assert tuple(slab.shape) == (n1, c, 4), f"slab shape {tuple(slab.shape)} != {(n1, c, 4)}"
+    ops.columns(slab, log_n, l1, lc, rank * c, inverse)
+    if world > 1:
+        recv = torch.empty_like(slab)
+        dist.all_to_all_single(recv.view(-1), slab.view(-1), group=group)   # row block h of every rank -> rank h
+    else:
+        recv = slab
+    rows = ops.unpack(recv, world, n1 // world, c)
+    from .scalar import R_MOD, fr
+    scale = fr(pow(1 << log_n, -1, R_MOD)) if inverse else None
+    ops.rows(rows, l2, inverse, scale)
+    return rows

@@ -304,3 +304,32 @@ def test_c4_batched_witness_full_size(gpu, cpu, full):
     ys_bad[17] = scalar.fr(scalar.fr_int(ys[17]) + 1)
     st, _, _ = gpu.witness_batched(srs, p, xs, ys_bad)
     assert st == gpu.KZGB_POINT_NOT_ON_POLYNOMIAL
+
+
+# ------------------------------------------------------------------ K8 four-step (multi-GPU) building blocks
+@pytest.mark.parametrize("log_n,world,inverse", [(8, 2, False), (12, 4, False), (12, 4, True), (16, 8, False), (20, 2, True)])
+def test_four_step_blocks_emulated_ranks(gpu, cpu, log_n, world, inverse):
+    """Runs every rank's local CUDA steps on this one GPU and performs the all-to-all by hand; the assembled result
+    must equal the single-GPU transform (and the oracle)."""
+    import torch
+    from kzg_b200 import distributed as kd
+    vec = cpu.fr_stream(5, 1 << log_n)
+    l1, l2, lc = kd.four_step_shape(log_n, world)
+    n1, c = 1 << l1, 1 << lc
+    ops = kd.CudaNttOps()
+    slabs = [torch.from_numpy(s.view(np.int64)).cuda() for s in kd.four_step_scatter(vec, log_n, world)]
+    for g in range(world):
+        ops.columns(slabs[g], log_n, l1, lc, g * c, inverse)
+    torch.cuda.synchronize()
+    blocks = []
+    for h in range(world):  # rank h receives row block h of every rank's slab
+        recv = torch.stack([slabs[g].view(world, n1 // world, c, 4)[h] for g in range(world)]).contiguous()
+        rows = ops.unpack(recv, world, n1 // world, c)
+        scale = scalar.fr(pow(1 << log_n, -1, R)) if inverse else None
+        ops.rows(rows, l2, inverse, scale)
+        torch.cuda.synchronize()
+        blocks.append(rows.cpu().numpy().view(np.uint64))
+    full = kd.four_step_gather(blocks, log_n, world)
+    assert (full == gpu.ntt(vec, log_n, inverse)[1]).all()
+    if log_n <= 16:
+        assert (full == cpu.fft(vec, log_n, inverse, 8)).all()
