@@ -9,7 +9,11 @@ OBJS := $(patsubst $(SRC_DIR)/%.cu,$(BUILD)/%.o,$(SRCS))
 HDRS := $(wildcard $(SRC_DIR)/*.cuh) include/kzg_b200.h
 LIB := kzg_b200/libkzg_b200.so
 
-all: $(LIB) oracle
+all: $(LIB) oracle $(BUILD)/host_mirror_demo
+
+# compile check of the header-only C++ host mirror (runs only on a GPU box)
+$(BUILD)/host_mirror_demo: tests/cpp/host_mirror_demo.cpp include/kzg_b200.hpp include/kzg_b200.h $(LIB)
+	g++ -std=c++17 -O2 -o $@ $< -Lkzg_b200 -lkzg_b200 -Wl,-rpath,'$$ORIGIN/../kzg_b200'
 
 $(BUILD)/%.o: $(SRC_DIR)/%.cu $(HDRS)
 	@mkdir -p $(BUILD)

@@ -231,6 +231,8 @@ def run_gpu(args):
     e2e_s = float(t.item())
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     stage_ms = {k: v[0] / v[1] for k, v in prof.items()}
     acc_ms = stage_ms.get("msm_accumulate")
@@ -318,6 +320,8 @@ def run_gpu(args):
         "gpu_launches": launches, "clocks": clk.summary(), "extra": extra,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():

@@ -163,7 +163,7 @@ KZGB_API const char* kzgb_profile_stage_name(int stage);
  * precedent: parallel_fft, ft.rs:336-387).  View the vector as N1 x N2 (index i1*N2 + i2).  Rank g holds the slab
  * [N1][C] of columns i2 in [g*C, (g+1)*C), C = N2/G.
  *   kzgb_ntt4_columns_dev: in place, N1-point transforms down the columns + twiddle omega_N^(k1*i2);
- *   (all-to-all of row blocks between ranks: done by the caller, e.g. torch.distributed / NCCL)
+ *   (all-to-all of row blocks between ranks: done by the caller over NCCL)
  *   kzgb_ntt4_unpack_dev : recv[g][r][c] -> rows[r][g*C + c];
  *   kzgb_ntt_batch_dev   : N2-point transforms of the N1/G local rows; row r of rank h then holds
  *                          X[(h*N1/G + r) + N1*k2], k2 = 0..N2-1. */

@@ -1,0 +1,68 @@
+"""torchrun script: sharded MSM parity (closed form) and four-step NTT 2^24 parity + timing across ranks."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from kzg_b200 import _ffi, distributed as kd, scalar
+from oracle import cpu
+
+rank, world, local = kd.init_process_group_from_env("nccl")
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+_ffi.init(local)
+LOG = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+# ---- sharded MSM over world * 2^18 points ----
+per = 1 << 18
+total = per * world
+s = cpu.fr_stream(69, 1)[0]
+srs = _ffi.srs_generate(0, s, total, first=rank * per, count=per)
+sc = torch.empty((per, 4), dtype=torch.int64, device=dev)
+_ffi.fr_stream_dev(sc.data_ptr(), 42, per, start=rank * per, stream=torch.cuda.current_stream().cuda_stream)
+out = kd.sharded_msm(srs, sc)
+torch.cuda.synchronize()
+if rank == 0:
+    coeffs = cpu.fr_stream(42, total)
+    expect = cpu.g1_to_affine(cpu.g1_mul(cpu.g1_generator(), cpu.poly_eval(coeffs, s)))[0]
+    print("sharded MSM parity (%d ranks, %d points):" % (world, total), bool((out.cpu().numpy().view(np.uint64) == expect).all()), flush=True)
+# ---- four-step NTT 2^LOG ----
+n = 1 << LOG
+l1, l2, lc = kd.four_step_shape(LOG, world)
+n1, c = 1 << l1, 1 << lc
+# generate this rank's slab directly: slab[i1][cc] = a[i1*N2 + rank*C + cc] ; build from the full stream on host (rank-local slices)
+full = cpu.fr_stream(5, n) if rank == 0 else None
+slab = torch.empty((n1, c, 4), dtype=torch.int64, device=dev)
+for i1 in range(n1):   # device-side generation row by row (stream positions are contiguous per row segment)
+    _ffi.fr_stream_dev(slab[i1].data_ptr(), 5, c, start=i1 * (1 << l2) + rank * c, stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+work = slab.clone()
+rows = kd.ntt_four_step(work, LOG, False)
+torch.cuda.synchronize()
+gathered = [torch.empty_like(rows) for _ in range(world)]
+dist.all_gather(gathered, rows) if world > 1 else gathered.__setitem__(0, rows)
+if rank == 0:
+    got = kd.four_step_gather([g.cpu().numpy().view(np.uint64) for g in gathered], LOG, world)
+    ref_t = torch.from_numpy(full.view(np.int64)).to(dev)
+    tmp = torch.empty_like(ref_t)
+    _ffi.ntt_dev(ref_t.data_ptr(), LOG, False, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    print("four-step NTT 2^%d parity vs single-GPU:" % LOG, bool((got == ref_t.cpu().numpy().view(np.uint64)).all()), flush=True)
+    del ref_t, tmp
+# timing (max over ranks)
+for _ in range(2):
+    work.copy_(slab); kd.ntt_four_step(work, LOG, False)
+if world > 1: dist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 5
+tot = 0.0
+for _ in range(K):
+    work.copy_(slab)
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    e0.record(); kd.ntt_four_step(work, LOG, False); e1.record()
+    torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+t = torch.tensor([tot / K], device=dev, dtype=torch.float64)
+if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("four-step NTT 2^%d on %d GPU(s): %.3f ms (max over ranks)" % (LOG, world, t.item()), flush=True)
+if world > 1: dist.destroy_process_group()
