@@ -49,6 +49,7 @@ struct FqParams {
         return t[i];
     }
     static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    __host__ __device__ static constexpr uint32_t inv32() { return INV; }
     // R = 2^384 mod p (Montgomery one)
     __host__ __device__ static constexpr uint32_t one(int i) {
         constexpr uint32_t t[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
@@ -63,6 +64,11 @@ struct FqParams {
     }
 };
 
+// -r^-1 mod 2^32 happens to be 0xffffffff.  As an immediate, ptxas strength-reduces m = t0 * 0xffffffff to a
+// negation and then no longer fuses the m*MOD products into IMAD.WIDE.U32.X (they become IMAD.HI + IMAD.X pairs:
+// +40 % FMA-heavy pipe cycles per Fr product).  Reading the constant from constant memory keeps it opaque.
+static __constant__ uint32_t FR_INV32_C[1] = {0xffffffffu};
+
 struct FrParams {
     static constexpr int N = 8;
     // r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
@@ -72,6 +78,7 @@ struct FrParams {
         return t[i];
     }
     static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    __device__ __forceinline__ static uint32_t inv32() { return FR_INV32_C[0]; }
     __host__ __device__ static constexpr uint32_t one(int i) {
         constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
                                         0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
@@ -164,6 +171,9 @@ struct Fe {
     KZG_DI friend Fe operator*(const Fe& a, const Fe& b) {
 #ifdef KZG_OUTLINE_FQ_MUL
         if constexpr (N == 12) return mul_outlined(a, b);
+#endif
+#ifdef KZG_OUTLINE_FR_MUL
+        if constexpr (N == 8) return mul_outlined(a, b);
 #endif
 #ifdef KZG_ROLLED_FQ_MUL
         if constexpr (N == 12) return mul_rolled(a, b);
@@ -268,7 +278,7 @@ struct Fe {
 
     // E + O*2^32 += m*MOD with m chosen so that limb 0 of E becomes zero.
     KZG_DI static void reduce_step(uint32_t* E, uint32_t* O) {
-        const uint32_t m = E[0] * P::INV;
+        const uint32_t m = E[0] * P::inv32();
         O[0] = mad_lo_cc(P::mod(1), m, O[0]);
         O[1] = madc_hi_cc(P::mod(1), m, O[1]);
 #pragma unroll

@@ -197,7 +197,7 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
 constexpr uint32_t FIX_F = 16;
 constexpr uint32_t FIX_PEEK = 4;
 
-__global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
+__global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
                                                               const PartialMeta* __restrict__ min_, uint32_t nslots_in,
                                                               XYZZ* __restrict__ buckets, XYZZ* __restrict__ pout,
                                                               PartialMeta* __restrict__ mout, uint32_t nthreads) {
@@ -279,44 +279,65 @@ KZG_DI XYZZ block_tree_sum(XYZZ acc, XYZZ* sh, int nthreads) {
     return sh[0];
 }
 
-__global__ void __launch_bounds__(RC_THREADS) msm_rowcol_sum_kernel(const XYZZ* __restrict__ buckets, uint32_t rows,
-                                                                    uint32_t cols, XYZZ* __restrict__ R,
-                                                                    XYZZ* __restrict__ C) {
-    __shared__ XYZZ sh[RC_THREADS];
-    XYZZ acc = XYZZ::inf();
-    if (blockIdx.x < rows) {
-        const uint32_t row = blockIdx.x;
-        const uint32_t per = (cols + RC_THREADS - 1) / RC_THREADS;
-        uint32_t j0 = threadIdx.x * per, j1 = min(j0 + per, cols);
-        for (uint32_t j = j0; j < j1; j++) {
-            XYZZ q = ld_xyzz(&buckets[(size_t)row * cols + j]);
-            xyzz_add(acc, q);
-        }
-        XYZZ tot = block_tree_sum(acc, sh, RC_THREADS);
-        if (threadIdx.x == 0) st_xyzz(&R[row], tot);
-    } else {
-        const uint32_t col = blockIdx.x - rows;
-        const uint32_t per = (rows + RC_THREADS - 1) / RC_THREADS;
-        uint32_t i0 = threadIdx.x * per, i1 = min(i0 + per, rows);
-        for (uint32_t i = i0; i < i1; i++) {
-            XYZZ q = ld_xyzz(&buckets[(size_t)i * cols + col]);
-            xyzz_add(acc, q);
-        }
-        XYZZ tot = block_tree_sum(acc, sh, RC_THREADS);
-        if (threadIdx.x == 0) st_xyzz(&C[col], tot);
+// Row sums and column sums by level-by-level pairwise additions: every lane of every warp performs one useful
+// addition per level (a serial chunk + shared-memory tree leaves half the lanes idle on most steps, and these
+// kernels are bound by warp-time on the FMA pipe).
+//   level 0:  Rb[hi][lo] = B[hi][lo] + B[hi][lo + cols/2]   (lo < cols/2)
+//             Cb[hi][lo] = B[hi][lo] + B[hi + rows/2][lo]   (hi < rows/2)
+//   level k:  Rb[hi][lo] += Rb[hi][lo + wr],  Cb[hi][lo] += Cb[hi + hc][lo]
+// The row stride of Rb stays cols/2 and that of Cb stays cols; R[hi] = Rb[hi][0], C[lo] = Cb[0][lo].
+__global__ void __launch_bounds__(128, 3) msm_pairsum_first_kernel(const XYZZ* __restrict__ B, uint32_t rows, uint32_t cols,
+                                                                XYZZ* __restrict__ Rb, XYZZ* __restrict__ Cb) {
+    const uint32_t half = (rows * cols) >> 1;
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < half) {  // R part
+        uint32_t hw = cols >> 1;
+        uint32_t hi = idx / hw, lo = idx % hw;
+        XYZZ a = ld_xyzz(&B[(size_t)hi * cols + lo]);
+        XYZZ b = ld_xyzz(&B[(size_t)hi * cols + lo + hw]);
+        xyzz_add(a, b);
+        st_xyzz(&Rb[idx], a);
+    } else if (idx < 2 * half) {  // C part
+        uint32_t j = idx - half;
+        uint32_t hi = j / cols, lo = j % cols;
+        XYZZ a = ld_xyzz(&B[(size_t)hi * cols + lo]);
+        XYZZ b = ld_xyzz(&B[(size_t)(hi + (rows >> 1)) * cols + lo]);
+        xyzz_add(a, b);
+        st_xyzz(&Cb[j], a);
+    }
+}
+// wr: number of live columns of Rb AFTER this level (0 = R is finished); hc likewise for the rows of Cb
+__global__ void __launch_bounds__(128, 3) msm_pairsum_level_kernel(XYZZ* __restrict__ Rb, uint32_t rows, uint32_t rstride,
+                                                                uint32_t wr, XYZZ* __restrict__ Cb, uint32_t cols,
+                                                                uint32_t hc) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nr = rows * wr;
+    if (idx < nr) {
+        uint32_t hi = idx / wr, lo = idx % wr;
+        XYZZ a = ld_xyzz(&Rb[(size_t)hi * rstride + lo]);
+        XYZZ b = ld_xyzz(&Rb[(size_t)hi * rstride + lo + wr]);
+        xyzz_add(a, b);
+        st_xyzz(&Rb[(size_t)hi * rstride + lo], a);
+    } else if (idx < nr + hc * cols) {
+        uint32_t j = idx - nr;
+        XYZZ a = ld_xyzz(&Cb[j]);
+        XYZZ b = ld_xyzz(&Cb[(size_t)hc * cols + j]);
+        xyzz_add(a, b);
+        st_xyzz(&Cb[j], a);
     }
 }
 
 // blocks [0, nbr): partial sums of hi * R[hi];  blocks [nbr, nbr+nbc): partial sums of (lo+1) * C[lo]
 constexpr int WS_THREADS = 128;
 __global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ* __restrict__ R, uint32_t rows,
-                                                                      const XYZZ* __restrict__ C, uint32_t cols,
-                                                                      uint32_t nbr, XYZZ* __restrict__ partial) {
+                                                                      uint32_t rstride, const XYZZ* __restrict__ C,
+                                                                      uint32_t cols, uint32_t nbr,
+                                                                      XYZZ* __restrict__ partial) {
     __shared__ XYZZ sh[WS_THREADS];
     XYZZ acc = XYZZ::inf();
     if (blockIdx.x < nbr) {
         uint32_t hi = blockIdx.x * WS_THREADS + threadIdx.x;
-        if (hi < rows && hi > 0) acc = xyzz_mul_small(ld_xyzz(&R[hi]), hi);
+        if (hi < rows && hi > 0) acc = xyzz_mul_small(ld_xyzz(&R[(size_t)hi * rstride]), hi);
     } else {
         uint32_t lo = (blockIdx.x - nbr) * WS_THREADS + threadIdx.x;
         if (lo < cols) acc = xyzz_mul_small(ld_xyzz(&C[lo]), lo + 1);
@@ -545,7 +566,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.off_fixp1 = take((size_t)p.fix_slots * sizeof(XYZZ));
     p.off_fixm0 = take((size_t)p.fix_slots * sizeof(PartialMeta));
     p.off_fixm1 = take((size_t)p.fix_slots * sizeof(PartialMeta));
-    p.off_red0 = take((size_t)(p.rows + p.cols) * sizeof(XYZZ));
+    p.off_red0 = take(((size_t)p.nb + 2) * sizeof(XYZZ));  // Rb (nb/2) then Cb (nb/2)
     p.off_red1 = take((size_t)(p.nbr + p.nbc) * sizeof(XYZZ));
     p.off_result = take(sizeof(XYZZ) * 2);
     p.cub_bytes = 0;
@@ -635,14 +656,46 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     }
     stage_end(ST_MSM_FIXUP, stream);
     stage_begin(ST_MSM_BUCKET_REDUCE, stream);
-    XYZZ* Rsum = red0;
-    XYZZ* Csum = red0 + p.rows;
-    msm_rowcol_sum_kernel<<<p.rows + p.cols, RC_THREADS, 0, stream>>>(buckets, p.rows, p.cols, Rsum, Csum);
-    KZG_LAUNCHED();
-    msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsum, p.rows, Csum, p.cols, p.nbr, red1);
-    KZG_LAUNCHED();
-    msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
-    KZG_LAUNCHED();
+    {
+        XYZZ* Rb = red0;
+        XYZZ* Cb = red0 + (p.nb >> 1) + 1;
+        const XYZZ* Rsrc = buckets;   // degenerate shapes: a single column / a single row need no summing
+        const XYZZ* Csrc = buckets;
+        uint32_t rstride = p.cols;
+        if (p.nb >= 2 && p.cols >= 2 && p.rows >= 2) {
+            msm_pairsum_first_kernel<<<div_up(p.nb, 128), 128, 0, stream>>>(buckets, p.rows, p.cols, Rb, Cb);
+            KZG_LAUNCHED();
+            rstride = p.cols >> 1;
+            uint32_t wr = p.cols >> 1, hc = p.rows >> 1;  // live extents after level 0
+            while (wr > 1 || hc > 1) {
+                uint32_t nwr = wr > 1 ? wr >> 1 : 0, nhc = hc > 1 ? hc >> 1 : 0;
+                uint32_t work = p.rows * nwr + nhc * p.cols;
+                msm_pairsum_level_kernel<<<div_up(work, 128), 128, 0, stream>>>(Rb, p.rows, rstride, nwr, Cb, p.cols, nhc);
+                KZG_LAUNCHED();
+                if (nwr) wr = nwr;
+                if (nhc) hc = nhc;
+            }
+            Rsrc = Rb;
+            Csrc = Cb;
+        } else if (p.cols == 1) {
+            // rows x 1: R[hi] = B[hi], C[0] = sum of all -> let the weighted kernel treat B as R only
+            rstride = 1;
+        }
+        if (p.cols == 1 || p.rows == 1) {
+            // tiny windows (c <= 2): fall back to weights on the flat bucket array: S = sum (b+1) B[b]
+            msm_weighted_sum_kernel<<<(p.nb + WS_THREADS - 1) / WS_THREADS, WS_THREADS, 0, stream>>>(
+                buckets, 0, 1, buckets, p.nb, 0, red1);
+            KZG_LAUNCHED();
+            msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, 0, (p.nb + WS_THREADS - 1) / WS_THREADS, 0, result);
+            KZG_LAUNCHED();
+        } else {
+            msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsrc, p.rows, rstride, Csrc, p.cols, p.nbr,
+                                                                            red1);
+            KZG_LAUNCHED();
+            msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
+            KZG_LAUNCHED();
+        }
+    }
     stage_end(ST_MSM_BUCKET_REDUCE, stream);
     stage_begin(ST_MSM_FINISH, stream);
     return KZGB_OK;

@@ -15,6 +15,9 @@
 // order; its tile is T consecutive k_1, so those writes are T*32 B contiguous
 // too.  One table omega_N^i (i < N/2) per domain serves both directions
 // (omega^-e = -omega^(N/2-e)), and every stage of every pass.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "field.cuh"
 #include "fr_util.cuh"
@@ -213,6 +216,15 @@ struct NttPlan {
 
 static NttPlan ntt_plan(uint32_t log_n) {
     NttPlan pl;
+    if (const char* e = getenv("KZGB_NTT_PLAN")) {  // experiment knob: "a,b[,c]" radices (must sum to log_n)
+        unsigned a = 0, b = 0, c = 0;
+        int k = sscanf(e, "%u,%u,%u", &a, &b, &c);
+        if (k >= 1 && a + b + c == log_n && a <= 11 && b <= 11 && c <= 11) {
+            pl.npass = k;
+            pl.log_r[0] = a; pl.log_r[1] = b; pl.log_r[2] = c;
+            return pl;
+        }
+    }
     if (log_n <= 10) {
         pl.npass = 1; pl.log_r[0] = log_n; pl.log_r[1] = pl.log_r[2] = 0;
     } else if (log_n <= 20) {
