@@ -23,6 +23,9 @@
 //               K6 XYZZ -> affine / Jacobian
 #include <cub/device/device_radix_sort.cuh>
 
+#ifndef KZG_MSM_NO_DEDICATED_SQR
+#define KZG_FQ_DEDICATED_SQR 1
+#endif
 #if defined(KZG_MSM_ROLLED_MUL)
 #define KZG_ROLLED_FQ_MUL 1
 #elif !defined(KZG_MSM_INLINE_MUL)

@@ -1,5 +1,6 @@
 // test_hooks.cu -- bulk element-wise entry points used by the parity tests to
 // pin the device field arithmetic against the oracle.
+#define KZG_FQ_DEDICATED_SQR 1
 #include "common.cuh"
 #include "field.cuh"
 

@@ -46,6 +46,7 @@ def test_field_ops_bit_exact(gpu, cpu):
     pm1 = np.array(O.fq_to_mont_limbs(O.P_MOD - 1), dtype=np.uint64)
     fa[0], fb[0], fa[1], fb[1] = pm1, pm1, 0, pm1
     assert (gpu.test_fp_op(fa, fb, 0) == cpu.fp_mul_vec(fa, fb)).all()
+    assert (gpu.test_fp_op(fa, None, 6) == cpu.fp_mul_vec(fa, fa)).all()      # dedicated squaring path
     for k in range(8):
         x, y = O.fq_from_mont_limbs(fa[k]), O.fq_from_mont_limbs(fb[k])
         assert O.fq_from_mont_limbs(gpu.test_fp_op(fa[k:k + 1], fb[k:k + 1], 1)[0]) == (x + y) % O.P_MOD
