@@ -212,9 +212,15 @@ __global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __r
     XYZZ acc = XYZZ::inf();
     uint32_t cur = SLOT_EMPTY, cur_start = 0;
     bool flushed_any = false;
-    for (uint32_t j = lo; j < hi; j++) {
+    // valid slots of the range as a bit mask (FIX_F + 1 <= 32 slots); lanes then walk their k-th valid slot
+    // together, so sparse levels pay one point addition per round instead of one per slot position
+    uint32_t mask = 0;
+    for (uint32_t j = lo; j < hi; j++)
+        if (min_[j].bucket != SLOT_EMPTY) mask |= 1u << (j - lo);
+    while (mask) {
+        uint32_t j = lo + (uint32_t)__ffs((int)mask) - 1;
+        mask &= mask - 1;
         PartialMeta mj = min_[j];
-        if (mj.bucket == SLOT_EMPTY) continue;
         if (cur != SLOT_EMPTY && (mj.bucket != cur || mj.is_start)) {
             // run `cur` ends here
             if (cur_start) {
