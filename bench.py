@@ -243,7 +243,7 @@ def run_gpu(args):
         achieved = IMAD_PER_POINT_ACC * N_POINTS / (acc_ms * 1e-3)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_msm_accumulate_summary.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01f_msm_accumulate_summary.json"))).get("dram_bytes_per_launch")
         except Exception:
             pass
         roofline = {"bound": "int32_imad", "kernel": "msm_accumulate_kernel", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
@@ -291,6 +291,27 @@ def run_gpu(args):
             st = _ffi.witness_coeff_dev(srs, polys[0].data_ptr(), N_POINTS, xy.data_ptr(), work.data_ptr(), wout.data_ptr(), stream)
         extra["witness_2p20_ms"] = (time.perf_counter() - t0) / 5 * 1e3
         extra["witness_status"] = st
+        # C4: create_witness_batched, 256 openings (interpolation + coset-NTT division + MSM), device resident
+        m = 256
+        xs_t = torch.empty((m, 4), dtype=torch.int64, device=dev)
+        _ffi.fr_stream_dev(xs_t.data_ptr(), 7, m, stream=stream)
+        ys_t = torch.empty((m, 4), dtype=torch.int64, device=dev)
+        xy1 = torch.zeros((2, 4), dtype=torch.int64, device=dev)
+        for i in range(m):  # y_i = p(x_i): remainders of linear scans
+            xy1[0] = xs_t[i]
+            lib.kzgb_divide_linear_dev(C.c_void_p(polys[0].data_ptr()), C.c_size_t(N_POINTS), C.c_void_p(xy1.data_ptr()), C.c_int(0),
+                                       C.c_void_p(work.data_ptr()), C.c_void_p(ys_t[i].data_ptr()), C.c_void_p(stream))
+        r_t = torch.zeros((m + 2, 4), dtype=torch.int64, device=dev)
+        for _ in range(2):
+            stb = _ffi.witness_batched_dev(srs, polys[0].data_ptr(), N_POINTS, xs_t.data_ptr(), ys_t.data_ptr(), m, r_t.data_ptr(), wout.data_ptr(), stream)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            stb = _ffi.witness_batched_dev(srs, polys[0].data_ptr(), N_POINTS, xs_t.data_ptr(), ys_t.data_ptr(), m, r_t.data_ptr(), wout.data_ptr(), stream)
+        extra["witness_batched_2p20_m256_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        extra["witness_batched_status"] = stb
+        # roofline of the same dominant kernel seen from HBM (for completeness; it is not the binding roof)
+        if acc_ms and peaks:
+            extra["accumulate_hbm_view"] = {"algorithmic_GBps": (N_POINTS * 13 * 104) / (acc_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak}
 
     cpu_baseline = None
     if world == 1:

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128, 3) msm_pairsum_level_kernel(XYZZ* __restr
 }
 
 // blocks [0, nbr): partial sums of hi * R[hi];  blocks [nbr, nbr+nbc): partial sums of (lo+1) * C[lo]
-constexpr int WS_THREADS = 128;
+constexpr int WS_THREADS = 256;
 __global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ* __restrict__ R, uint32_t rows,
                                                                       uint32_t rstride, const XYZZ* __restrict__ C,
                                                                       uint32_t cols, uint32_t nbr,
@@ -358,13 +358,23 @@ __global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ
 // result = 2^log_cols * (sum of the first nbr partials) + (sum of the remaining nbc partials)
 __global__ void msm_reduce_final_kernel(const XYZZ* __restrict__ partial, uint32_t nbr, uint32_t nbc, uint32_t log_cols,
                                         XYZZ* __restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
-    XYZZ vr = XYZZ::inf(), vc = XYZZ::inf();
-    for (uint32_t i = 0; i < nbr; i++) { XYZZ q = ld_xyzz(&partial[i]); xyzz_add(vr, q); }
-    for (uint32_t i = 0; i < nbc; i++) { XYZZ q = ld_xyzz(&partial[nbr + i]); xyzz_add(vc, q); }
-    for (uint32_t i = 0; i < log_cols; i++) vr = xyzz_dbl(vr);
-    xyzz_add(vr, vc);
-    st_xyzz(out, vr);
+    // lane 0 folds the row partials and applies the 2^log_cols factor while lane 1 folds the column partials
+    __shared__ XYZZ sh[2];
+    if (blockIdx.x || threadIdx.x > 1) return;
+    XYZZ v = XYZZ::inf();
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < nbr; i++) { XYZZ q = ld_xyzz(&partial[i]); xyzz_add(v, q); }
+        for (uint32_t i = 0; i < log_cols; i++) v = xyzz_dbl(v);
+    } else {
+        for (uint32_t i = 0; i < nbc; i++) { XYZZ q = ld_xyzz(&partial[nbr + i]); xyzz_add(v, q); }
+    }
+    sh[threadIdx.x] = v;
+    __syncwarp(0x3);
+    if (threadIdx.x == 0) {
+        XYZZ c = sh[1];
+        xyzz_add(v, c);
+        st_xyzz(out, v);
+    }
 }
 
 // K6: result conversion.  mode 0: affine (blst_p1_affine), 1: Jacobian (blst_p1), 2: raw XYZZ
