@@ -186,6 +186,105 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
     meta[2 * (size_t)t + 1] = m1;
 }
 
+
+// --------------------------------------------------------------------------
+// 4-lane cooperative point arithmetic for the latency-bound tail kernels.
+// The 14 field multiplications of an XYZZ addition have dependency depth 4 (and the 9 of a doubling depth 3), but a
+// single thread issues them back to back (~0.6 us each).  Four adjacent lanes hold the SAME operands, each computes
+// one product per step and the results are exchanged with shuffles: ~3x lower latency per point operation at 4x the
+// lanes -- the right trade where a kernel has far fewer additions than the chip has lanes.
+// --------------------------------------------------------------------------
+KZG_DI Fq grp_bcast(const Fq& v, int src, unsigned gmask) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_sync(gmask, v.l[i], src, 4);
+    return r;
+}
+KZG_DI Fq sel4(int r, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
+    Fq o;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o.l[i] = r == 0 ? a0.l[i] : (r == 1 ? a1.l[i] : (r == 2 ? a2.l[i] : a3.l[i]));
+    return o;
+}
+KZG_DI unsigned grp_mask() { return 0xfu << (threadIdx.x & 28); }
+
+// acc += q; all four lanes of the group pass identical acc and q and all receive the result
+__device__ __noinline__ void xyzz_add_coop(XYZZ& acc, const XYZZ& q) {
+    if (q.is_inf()) return;
+    if (acc.is_inf()) { acc = q; return; }
+    const unsigned gm = grp_mask();
+    const int r = threadIdx.x & 3;
+    Fq m = sel4(r, acc.x, q.x, acc.y, q.y) * sel4(r, q.zz, acc.zz, q.zzz, acc.zzz);
+    Fq U1 = grp_bcast(m, 0, gm), U2 = grp_bcast(m, 1, gm), S1 = grp_bcast(m, 2, gm), S2 = grp_bcast(m, 3, gm);
+    Fq P = U2 - U1, R = S2 - S1;
+    if (P.is_zero()) {  // equal or opposite points: rare, take the single-thread path (uniform across the group)
+        xyzz_add(acc, q);
+        return;
+    }
+    m = sel4(r, P, R, acc.zz, acc.zzz) * sel4(r, P, R, q.zz, q.zzz);
+    Fq PP = grp_bcast(m, 0, gm), RR = grp_bcast(m, 1, gm), ZZ12 = grp_bcast(m, 2, gm), ZZZ12 = grp_bcast(m, 3, gm);
+    m = sel4(r, P, U1, ZZ12, ZZ12) * PP;
+    Fq PPP = grp_bcast(m, 0, gm), Q = grp_bcast(m, 1, gm);
+    acc.zz = grp_bcast(m, 2, gm);
+    Fq X3 = RR - PPP - Q.dbl();
+    m = sel4(r, R, S1, ZZZ12, ZZZ12) * sel4(r, Q - X3, PPP, PPP, PPP);
+    Fq t1 = grp_bcast(m, 0, gm), t2 = grp_bcast(m, 1, gm);
+    acc.zzz = grp_bcast(m, 2, gm);
+    acc.x = X3;
+    acc.y = t1 - t2;
+}
+
+// p = 2p, cooperative
+__device__ __noinline__ void xyzz_dbl_coop(XYZZ& p) {
+    if (p.is_inf() || p.y.is_zero()) { p = XYZZ::inf(); return; }
+    const unsigned gm = grp_mask();
+    const int r = threadIdx.x & 3;
+    Fq U = p.y.dbl();
+    Fq a = sel4(r, U, p.x, U, U);
+    Fq m = a * a;
+    Fq V = grp_bcast(m, 0, gm), XX = grp_bcast(m, 1, gm);
+    Fq M = XX.dbl() + XX;
+    m = sel4(r, U, p.x, V, M) * sel4(r, V, V, p.zz, M);
+    Fq W = grp_bcast(m, 0, gm), S = grp_bcast(m, 1, gm), ZZ3 = grp_bcast(m, 2, gm), MM = grp_bcast(m, 3, gm);
+    Fq X3 = MM - S.dbl();
+    m = sel4(r, M, W, W, W) * sel4(r, S - X3, p.y, p.zzz, p.zzz);
+    Fq t1 = grp_bcast(m, 0, gm), t2 = grp_bcast(m, 1, gm);
+    p.zzz = grp_bcast(m, 2, gm);
+    p.zz = ZZ3;
+    p.x = X3;
+    p.y = t1 - t2;
+}
+
+// k * p (k uniform across the group)
+KZG_DI XYZZ xyzz_mul_small_coop(const XYZZ& p, uint32_t k) {
+    XYZZ acc = XYZZ::inf();
+    for (int i = 31 - __clz(k | 1); i >= 0; i--) {
+        xyzz_dbl_coop(acc);
+        if ((k >> i) & 1) xyzz_add_coop(acc, p);
+    }
+    return acc;
+}
+
+// tree sum of one value per 4-lane group over a block of NT threads (NT/4 groups); result in every lane of group 0
+template <int NT>
+KZG_DI XYZZ block_tree_sum_coop(XYZZ v, XYZZ* sh /* NT/4 entries */) {
+    const int g = threadIdx.x >> 2, r = threadIdx.x & 3;
+    if (r == 0) sh[g] = v;
+    __syncthreads();
+    for (int s = NT / 8; s > 0; s >>= 1) {
+        if (g < s) {
+            XYZZ a = sh[g];
+            XYZZ b = sh[g + s];
+            xyzz_add_coop(a, b);
+            v = a;
+        }
+        __syncthreads();
+        if (g < s && r == 0) sh[g] = v;
+        __syncthreads();
+    }
+    return sh[0];
+}
+
 // K4b: hierarchical segmented reduction of the chunk-boundary partial sums.
 // The slot list (2 per producing thread, in sorted-bucket order) is cut into runs: a run starts at a slot with
 // is_start and continues over following slots of the same bucket (EMPTY slots are skipped).  Each thread owns
@@ -200,11 +299,17 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
 constexpr uint32_t FIX_F = 16;
 constexpr uint32_t FIX_PEEK = 4;
 
-__global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
+template <bool COOP>
+__global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
                                                               const PartialMeta* __restrict__ min_, uint32_t nslots_in,
                                                               XYZZ* __restrict__ buckets, XYZZ* __restrict__ pout,
                                                               PartialMeta* __restrict__ mout, uint32_t nthreads) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    // COOP: one 4-lane group per range (the four lanes run the same control flow on the same data, lane 0 stores) --
+    // used from level 1 on, where partials are sparse and latency is all that matters; level 0 is dense and uses
+    // one thread per range.
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = COOP ? gt >> 2 : gt;
+    const bool lead = COOP ? (threadIdx.x & 3) == 0 : true;
     if (t >= nthreads) return;
     uint32_t lo = t ? t * FIX_F + 1 : 0;
     uint32_t hi = min((t + 1) * FIX_F + 1, nslots_in);
@@ -224,9 +329,9 @@ __global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __r
         if (cur != SLOT_EMPTY && (mj.bucket != cur || mj.is_start)) {
             // run `cur` ends here
             if (cur_start) {
-                st_xyzz(&buckets[cur], acc);
+                if (lead) st_xyzz(&buckets[cur], acc);
             } else {  // continues a run from an earlier thread: only possible for the first run
-                st_xyzz(&pout[2 * (size_t)t], acc);
+                if (lead) st_xyzz(&pout[2 * (size_t)t], acc);
                 m0 = PartialMeta{cur, 0};
             }
             flushed_any = true;
@@ -235,7 +340,8 @@ __global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __r
         }
         if (cur == SLOT_EMPTY) { cur = mj.bucket; cur_start = mj.is_start; }
         XYZZ q = ld_xyzz(&pin[j]);
-        xyzz_add(acc, q);
+        if (COOP) xyzz_add_coop(acc, q);
+        else xyzz_add(acc, q);
     }
     if (cur != SLOT_EMPTY) {
         // does the run end at the range boundary?
@@ -249,17 +355,19 @@ __global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __r
             break;
         }
         if (known && ended && cur_start) {
-            st_xyzz(&buckets[cur], acc);
+            if (lead) st_xyzz(&buckets[cur], acc);
         } else if (!flushed_any) {
-            st_xyzz(&pout[2 * (size_t)t], acc);
+            if (lead) st_xyzz(&pout[2 * (size_t)t], acc);
             m0 = PartialMeta{cur, cur_start};
         } else {
-            st_xyzz(&pout[2 * (size_t)t + 1], acc);
+            if (lead) st_xyzz(&pout[2 * (size_t)t + 1], acc);
             m1 = PartialMeta{cur, cur_start};
         }
     }
-    mout[2 * (size_t)t] = m0;
-    mout[2 * (size_t)t + 1] = m1;
+    if (lead) {
+        mout[2 * (size_t)t] = m0;
+        mout[2 * (size_t)t + 1] = m1;
+    }
 }
 
 // --------------------------------------------------------------------------
@@ -272,6 +380,7 @@ __global__ void __launch_bounds__(128, 3) msm_fixup_level_kernel(const XYZZ* __r
 // buckets -- single-thread point additions cost ~8 us each, so the serial chain length IS the latency.
 // --------------------------------------------------------------------------
 constexpr int RC_THREADS = 64;
+constexpr uint32_t MSM_COOP_THRESHOLD = 148 * 4 * 32;  // additions per level below which lanes are plentiful
 
 KZG_DI XYZZ block_tree_sum(XYZZ acc, XYZZ* sh, int nthreads) {
     sh[threadIdx.x] = acc;
@@ -336,44 +445,74 @@ __global__ void __launch_bounds__(128, 3) msm_pairsum_level_kernel(XYZZ* __restr
     }
 }
 
-// blocks [0, nbr): partial sums of hi * R[hi];  blocks [nbr, nbr+nbc): partial sums of (lo+1) * C[lo]
-constexpr int WS_THREADS = 256;
+// Same level as msm_pairsum_level_kernel with one 4-lane group per addition (used once a level has too few additions
+// to fill the chip: latency, not throughput, is what such a level costs).
+__global__ void __launch_bounds__(128) msm_pairsum_level_coop_kernel(XYZZ* __restrict__ Rb, uint32_t rows, uint32_t rstride,
+                                                                     uint32_t wr, XYZZ* __restrict__ Cb, uint32_t cols,
+                                                                     uint32_t hc) {
+    uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool lead = (threadIdx.x & 3) == 0;
+    const uint32_t nr = rows * wr;
+    if (idx < nr) {
+        uint32_t hi = idx / wr, lo = idx % wr;
+        XYZZ a = ld_xyzz(&Rb[(size_t)hi * rstride + lo]);
+        XYZZ b = ld_xyzz(&Rb[(size_t)hi * rstride + lo + wr]);
+        xyzz_add_coop(a, b);
+        if (lead) st_xyzz(&Rb[(size_t)hi * rstride + lo], a);
+    } else if (idx < nr + hc * cols) {
+        uint32_t j = idx - nr;
+        XYZZ a = ld_xyzz(&Cb[j]);
+        XYZZ b = ld_xyzz(&Cb[(size_t)hc * cols + j]);
+        xyzz_add_coop(a, b);
+        if (lead) st_xyzz(&Cb[j], a);
+    }
+}
+
+// One 4-lane group per row / column: hi * R[hi] or (lo+1) * C[lo] by cooperative double-and-add, then a cooperative
+// tree sum over the block's 32 groups.  blocks [0, nbr): rows, blocks [nbr, nbr+nbc): columns.
+constexpr int WS_THREADS = 128;
+constexpr int WS_GROUPS = WS_THREADS / 4;
 __global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ* __restrict__ R, uint32_t rows,
                                                                       uint32_t rstride, const XYZZ* __restrict__ C,
                                                                       uint32_t cols, uint32_t nbr,
                                                                       XYZZ* __restrict__ partial) {
-    __shared__ XYZZ sh[WS_THREADS];
+    __shared__ XYZZ sh[WS_GROUPS];
+    const uint32_t g = threadIdx.x >> 2;
     XYZZ acc = XYZZ::inf();
     if (blockIdx.x < nbr) {
-        uint32_t hi = blockIdx.x * WS_THREADS + threadIdx.x;
-        if (hi < rows && hi > 0) acc = xyzz_mul_small(ld_xyzz(&R[(size_t)hi * rstride]), hi);
+        uint32_t hi = blockIdx.x * WS_GROUPS + g;
+        if (hi < rows && hi > 0) acc = xyzz_mul_small_coop(ld_xyzz(&R[(size_t)hi * rstride]), hi);
     } else {
-        uint32_t lo = (blockIdx.x - nbr) * WS_THREADS + threadIdx.x;
-        if (lo < cols) acc = xyzz_mul_small(ld_xyzz(&C[lo]), lo + 1);
+        uint32_t lo = (blockIdx.x - nbr) * WS_GROUPS + g;
+        if (lo < cols) acc = xyzz_mul_small_coop(ld_xyzz(&C[lo]), lo + 1);
     }
-    XYZZ tot = block_tree_sum(acc, sh, WS_THREADS);
+    XYZZ tot = block_tree_sum_coop<WS_THREADS>(acc, sh);
     if (threadIdx.x == 0) st_xyzz(&partial[blockIdx.x], tot);
 }
 
-// result = 2^log_cols * (sum of the first nbr partials) + (sum of the remaining nbc partials)
-__global__ void msm_reduce_final_kernel(const XYZZ* __restrict__ partial, uint32_t nbr, uint32_t nbc, uint32_t log_cols,
-                                        XYZZ* __restrict__ out) {
-    // lane 0 folds the row partials and applies the 2^log_cols factor while lane 1 folds the column partials
-    __shared__ XYZZ sh[2];
-    if (blockIdx.x || threadIdx.x > 1) return;
-    XYZZ v = XYZZ::inf();
-    if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < nbr; i++) { XYZZ q = ld_xyzz(&partial[i]); xyzz_add(v, q); }
-        for (uint32_t i = 0; i < log_cols; i++) v = xyzz_dbl(v);
-    } else {
-        for (uint32_t i = 0; i < nbc; i++) { XYZZ q = ld_xyzz(&partial[nbr + i]); xyzz_add(v, q); }
+// result = 2^log_cols * (sum of the first nbr partials) + (sum of the remaining nbc partials); one block, cooperative
+__global__ void __launch_bounds__(WS_THREADS) msm_reduce_final_kernel(const XYZZ* __restrict__ partial, uint32_t nbr,
+                                                                      uint32_t nbc, uint32_t log_cols,
+                                                                      XYZZ* __restrict__ out) {
+    __shared__ XYZZ sh[WS_GROUPS];
+    __shared__ XYZZ vr_s;
+    const uint32_t g = threadIdx.x >> 2;
+    XYZZ acc = XYZZ::inf();
+    for (uint32_t i = g; i < nbr; i += WS_GROUPS) { XYZZ q = ld_xyzz(&partial[i]); xyzz_add_coop(acc, q); }
+    XYZZ vr = block_tree_sum_coop<WS_THREADS>(acc, sh);
+    __syncthreads();
+    if (g == 0) {
+        for (uint32_t i = 0; i < log_cols; i++) xyzz_dbl_coop(vr);
+        if (threadIdx.x == 0) vr_s = vr;
     }
-    sh[threadIdx.x] = v;
-    __syncwarp(0x3);
-    if (threadIdx.x == 0) {
-        XYZZ c = sh[1];
-        xyzz_add(v, c);
-        st_xyzz(out, v);
+    __syncthreads();
+    acc = XYZZ::inf();
+    for (uint32_t i = g; i < nbc; i += WS_GROUPS) { XYZZ q = ld_xyzz(&partial[nbr + i]); xyzz_add_coop(acc, q); }
+    XYZZ vc = block_tree_sum_coop<WS_THREADS>(acc, sh);
+    if (g == 0) {
+        XYZZ v = vr_s;
+        xyzz_add_coop(v, vc);
+        if (threadIdx.x == 0) st_xyzz(out, v);
     }
 }
 
@@ -567,8 +706,8 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.log_cols = (uint32_t)(s->c - 1) / 2;
     p.cols = 1u << p.log_cols;
     p.rows = p.nb >> p.log_cols;
-    p.nbr = (p.rows + WS_THREADS - 1) / WS_THREADS;
-    p.nbc = (p.cols + WS_THREADS - 1) / WS_THREADS;
+    p.nbr = (p.rows + WS_GROUPS - 1) / WS_GROUPS;
+    p.nbc = (p.cols + WS_GROUPS - 1) / WS_GROUPS;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     p.off_keys0 = take(p.total * 4);
@@ -661,10 +800,14 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
         XYZZ* pbuf[2] = {(XYZZ*)(w + p.off_fixp0), (XYZZ*)(w + p.off_fixp1)};
         PartialMeta* mbuf[2] = {(PartialMeta*)(w + p.off_fixm0), (PartialMeta*)(w + p.off_fixm1)};
         int which = 0;
-        for (;;) {
+        for (int level = 0;; level++) {
             uint32_t nth = nslots_in > 1 ? (nslots_in - 1 + FIX_F - 1) / FIX_F : 1;
-            msm_fixup_level_kernel<<<div_up(nth, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets, pbuf[which],
-                                                                         mbuf[which], nth);
+            if (level == 0)
+                msm_fixup_level_kernel<false><<<div_up(nth, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets,
+                                                                                    pbuf[which], mbuf[which], nth);
+            else
+                msm_fixup_level_kernel<true><<<div_up((size_t)nth * 4, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets,
+                                                                                         pbuf[which], mbuf[which], nth);
             KZG_LAUNCHED();
             if (nth == 1) break;
             pin = pbuf[which];
@@ -689,7 +832,12 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
             while (wr > 1 || hc > 1) {
                 uint32_t nwr = wr > 1 ? wr >> 1 : 0, nhc = hc > 1 ? hc >> 1 : 0;
                 uint32_t work = p.rows * nwr + nhc * p.cols;
-                msm_pairsum_level_kernel<<<div_up(work, 128), 128, 0, stream>>>(Rb, p.rows, rstride, nwr, Cb, p.cols, nhc);
+                if (work >= 4 * MSM_COOP_THRESHOLD)
+                    msm_pairsum_level_kernel<<<div_up(work, 128), 128, 0, stream>>>(Rb, p.rows, rstride, nwr, Cb, p.cols,
+                                                                                    nhc);
+                else
+                    msm_pairsum_level_coop_kernel<<<div_up((size_t)work * 4, 128), 128, 0, stream>>>(Rb, p.rows, rstride,
+                                                                                                nwr, Cb, p.cols, nhc);
                 KZG_LAUNCHED();
                 if (nwr) wr = nwr;
                 if (nhc) hc = nhc;
@@ -702,16 +850,16 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
         }
         if (p.cols == 1 || p.rows == 1) {
             // tiny windows (c <= 2): fall back to weights on the flat bucket array: S = sum (b+1) B[b]
-            msm_weighted_sum_kernel<<<(p.nb + WS_THREADS - 1) / WS_THREADS, WS_THREADS, 0, stream>>>(
+            msm_weighted_sum_kernel<<<(p.nb + WS_GROUPS - 1) / WS_GROUPS, WS_THREADS, 0, stream>>>(
                 buckets, 0, 1, buckets, p.nb, 0, red1);
             KZG_LAUNCHED();
-            msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, 0, (p.nb + WS_THREADS - 1) / WS_THREADS, 0, result);
+            msm_reduce_final_kernel<<<1, WS_THREADS, 0, stream>>>(red1, 0, (p.nb + WS_GROUPS - 1) / WS_GROUPS, 0, result);
             KZG_LAUNCHED();
         } else {
             msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsrc, p.rows, rstride, Csrc, p.cols, p.nbr,
                                                                             red1);
             KZG_LAUNCHED();
-            msm_reduce_final_kernel<<<1, 32, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
+            msm_reduce_final_kernel<<<1, WS_THREADS, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
             KZG_LAUNCHED();
         }
     }
