@@ -209,7 +209,7 @@ KZG_DI Fq sel4(int r, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
 KZG_DI unsigned grp_mask() { return 0xfu << (threadIdx.x & 28); }
 
 // acc += q; all four lanes of the group pass identical acc and q and all receive the result
-__device__ __noinline__ void xyzz_add_coop(XYZZ& acc, const XYZZ& q) {
+KZG_DI void xyzz_add_coop(XYZZ& acc, const XYZZ& q) {
     if (q.is_inf()) return;
     if (acc.is_inf()) { acc = q; return; }
     const unsigned gm = grp_mask();
@@ -235,7 +235,7 @@ __device__ __noinline__ void xyzz_add_coop(XYZZ& acc, const XYZZ& q) {
 }
 
 // p = 2p, cooperative
-__device__ __noinline__ void xyzz_dbl_coop(XYZZ& p) {
+KZG_DI void xyzz_dbl_coop(XYZZ& p) {
     if (p.is_inf() || p.y.is_zero()) { p = XYZZ::inf(); return; }
     const unsigned gm = grp_mask();
     const int r = threadIdx.x & 3;
@@ -255,12 +255,15 @@ __device__ __noinline__ void xyzz_dbl_coop(XYZZ& p) {
     p.y = t1 - t2;
 }
 
-// k * p (k uniform across the group)
-KZG_DI XYZZ xyzz_mul_small_coop(const XYZZ& p, uint32_t k) {
+// k * p for k < 2^nbits (k uniform across the group).  The loop is the same for every group of the warp (fixed trip
+// count, the addend is the identity where the bit is clear) so that groups do not serialise on divergent calls.
+KZG_DI XYZZ xyzz_mul_small_coop(const XYZZ& p, uint32_t k, int nbits) {
     XYZZ acc = XYZZ::inf();
-    for (int i = 31 - __clz(k | 1); i >= 0; i--) {
+#pragma unroll 1
+    for (int i = nbits - 1; i >= 0; i--) {
         xyzz_dbl_coop(acc);
-        if ((k >> i) & 1) xyzz_add_coop(acc, p);
+        XYZZ q = ((k >> i) & 1) ? p : XYZZ::inf();
+        xyzz_add_coop(acc, q);
     }
     return acc;
 }
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __rest
 // buckets -- single-thread point additions cost ~8 us each, so the serial chain length IS the latency.
 // --------------------------------------------------------------------------
 constexpr int RC_THREADS = 64;
-constexpr uint32_t MSM_COOP_THRESHOLD = 148 * 4 * 32;  // additions per level below which lanes are plentiful
+constexpr uint32_t MSM_COOP_THRESHOLD = 4096;  // additions per level below which lanes are plentiful (x4)
 
 KZG_DI XYZZ block_tree_sum(XYZZ acc, XYZZ* sh, int nthreads) {
     sh[threadIdx.x] = acc;
@@ -478,14 +481,19 @@ __global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_kernel(const XYZZ
                                                                       XYZZ* __restrict__ partial) {
     __shared__ XYZZ sh[WS_GROUPS];
     const uint32_t g = threadIdx.x >> 2;
-    XYZZ acc = XYZZ::inf();
+    XYZZ base = XYZZ::inf();
+    uint32_t k = 0;
+    int nbits;
     if (blockIdx.x < nbr) {
         uint32_t hi = blockIdx.x * WS_GROUPS + g;
-        if (hi < rows && hi > 0) acc = xyzz_mul_small_coop(ld_xyzz(&R[(size_t)hi * rstride]), hi);
+        if (hi < rows && hi > 0) { base = ld_xyzz(&R[(size_t)hi * rstride]); k = hi; }
+        nbits = 32 - __clz(rows | 1);
     } else {
         uint32_t lo = (blockIdx.x - nbr) * WS_GROUPS + g;
-        if (lo < cols) acc = xyzz_mul_small_coop(ld_xyzz(&C[lo]), lo + 1);
+        if (lo < cols) { base = ld_xyzz(&C[lo]); k = lo + 1; }
+        nbits = 32 - __clz(cols | 1);
     }
+    XYZZ acc = xyzz_mul_small_coop(base, k, nbits);
     XYZZ tot = block_tree_sum_coop<WS_THREADS>(acc, sh);
     if (threadIdx.x == 0) st_xyzz(&partial[blockIdx.x], tot);
 }
