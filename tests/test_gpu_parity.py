@@ -122,10 +122,14 @@ def test_msm_edge_cases(gpu, cpu):
     assert not gpu.SRS.from_jacobian(pair).msm(negone).any()
     with pytest.raises(gpu.KZGBackendError):
         srs.msm(np.zeros((n + 1, 4), dtype=np.uint64))                   # more scalars than points
+    assert not srs.msm(np.zeros((0, 4), dtype=np.uint64)).any()          # empty MSM -> identity
+    one_pt = gpu.SRS.from_jacobian(gs[:1])                               # single-point SRS: gs[0] * k
+    k = cpu.fr_stream(11, 1)
+    assert (one_pt.msm(k) == cpu.g1_to_affine(cpu.g1_mul(gs[0], k[0]))[0]).all()
 
 
 # ------------------------------------------------------------------ K7 NTT
-@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 10, 11, 13, 16])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 9, 10, 11, 12, 13, 15, 16, 17, 19, 21])
 def test_ntt_matches_oracle(gpu, cpu, log_n):
     a = cpu.fr_stream(5, 1 << log_n)
     st, f = gpu.ntt(a, log_n, False)
@@ -334,3 +338,39 @@ def test_four_step_blocks_emulated_ranks(gpu, cpu, log_n, world, inverse):
     assert (full == gpu.ntt(vec, log_n, inverse)[1]).all()
     if log_n <= 16:
         assert (full == cpu.fft(vec, log_n, inverse, 8)).all()
+
+
+def test_batched_witness_more_points_than_coefficients(gpu, cpu):
+    """coeff_form.rs:377-398 generalised: m >= n openings of a degree-(n-1) polynomial -> psi = 0, identity witness;
+    a wrong value is still rejected (numerator of degree < m must be the zero polynomial)."""
+    s = cpu.fr_stream(69, 1)[0]
+    srs = gpu.srs_generate(0, s, 64)
+    for n, m in ((40, 40), (17, 50), (1, 3)):
+        p = cpu.fr_stream(42, n)
+        xs = cpu.fr_stream(7, m)
+        ys = np.vstack([cpu.poly_eval(p, xs[i]) for i in range(m)])
+        st, r, w = gpu.witness_batched(srs, p, xs, ys)
+        assert st == 0 and not w.any() and len(r) == m
+        ys[m // 2] = scalar.fr(scalar.fr_int(ys[m // 2]) + 1)
+        assert gpu.witness_batched(srs, p, xs, ys)[0] == gpu.KZGB_POINT_NOT_ON_POLYNOMIAL
+
+
+def test_batched_witness_stale_degree_and_adversarial_coset_point(gpu, cpu):
+    """x_i on the first coset 7*H forces the device to pick another shift; the result must not change."""
+    s_i = O.fr_stream(69, 1)[0]
+    n = 256
+    srs = gpu.srs_generate(0, scalar.fr(s_i), n)
+    p_i = O.fr_stream(42, n)
+    omega = O.compute_omega(n)[2]
+    xs_i = [7 * pow(omega, 5, R) % R, 49 * pow(omega, 9, R) % R] + O.fr_stream(7, 6)   # two points on cosets 7H, 49H
+    poly = O.Polynomial.new(p_i)
+    ys_i = [poly.eval(x) for x in xs_i]
+    st, r, w = gpu.witness_batched(srs, scalar.fr_vec(p_i), scalar.fr_vec(xs_i), scalar.fr_vec(ys_i))
+    tree = O.SubProductTree.new_from_points(xs_i)
+    ref = O.Polynomial.lagrange_interpolation_with_tree(xs_i, ys_i, tree)
+    z = 1
+    for x in xs_i:
+        z = z * (s_i - x) % R
+    k = (poly.eval(s_i) - ref.eval(s_i)) * pow(z, -1, R) % R
+    assert st == 0 and scalar.fr_vec_int(r) == ref.coeffs[: ref.degree + 1]
+    assert (w == closed_form_point(cpu, scalar.fr(k))).all()
