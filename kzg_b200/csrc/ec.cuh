@@ -49,6 +49,19 @@ KZG_DI void stg_fq(Fq* p, const Fq& a) {
     for (int i = 0; i < 3; i++) q[i] = make_uint4(a.l[4 * i], a.l[4 * i + 1], a.l[4 * i + 2], a.l[4 * i + 3]);
 }
 KZG_DI Affine ldg_affine(const Affine* p) { return Affine{ldg_fq(&p->x), ldg_fq(&p->y)}; }
+// streaming gather (evict-first): table points are touched once per MSM, keep them from displacing the sequentially
+// read key/value lines in L1
+KZG_DI Fq ldcs_fq(const Fq* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        uint4 v = __ldcs(q + i);
+        r.l[4 * i] = v.x; r.l[4 * i + 1] = v.y; r.l[4 * i + 2] = v.z; r.l[4 * i + 3] = v.w;
+    }
+    return r;
+}
+KZG_DI Affine ldcs_affine(const Affine* p) { return Affine{ldcs_fq(&p->x), ldcs_fq(&p->y)}; }
 KZG_DI void stg_affine(Affine* p, const Affine& a) { stg_fq(&p->x, a.x); stg_fq(&p->y, a.y); }
 KZG_DI XYZZ ld_xyzz(const XYZZ* p) {
     const uint4* q = reinterpret_cast<const uint4*>(p);

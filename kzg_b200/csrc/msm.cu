@@ -141,7 +141,7 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
         XYZZ acc = XYZZ::inf();
         // software pipeline: the next point is in flight while the current one is added
         uint32_t v = vals[start];
-        Affine p = ldg_affine(&table[v & 0x7fffffffu]);
+        Affine p = ldcs_affine(&table[v & 0x7fffffffu]);
         for (uint64_t pos = start; pos < end; pos++) {
             uint32_t k = cur, vn = 0;
             Affine pn = p;
@@ -149,7 +149,7 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
             if (more) {
                 k = keys[pos + 1];
                 vn = vals[pos + 1];
-                pn = ldg_affine(&table[vn & 0x7fffffffu]);
+                pn = ldcs_affine(&table[vn & 0x7fffffffu]);
             }
             if (!p.is_inf()) {
                 Fq y = (v >> 31) ? p.y.neg() : p.y;

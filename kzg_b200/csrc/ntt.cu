@@ -66,6 +66,21 @@ KZG_DI Fr ldg_fr(const Fr* p) {
     return r;
 }
 
+// Shared-memory tile layout: the low and high 16-byte halves of element e live in separate planes
+// (plane h at byte offset h * 16 * E), so consecutive lanes touch consecutive 16-byte slots: with 32-byte AoS
+// elements every LDS.128/STS.128 of a warp had a 32-byte lane stride and was a 2-way bank conflict.
+KZG_DI Fr sm_ld(const uint4* sm, uint32_t e, uint32_t E) {
+    uint4 a = sm[e], b = sm[E + e];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+KZG_DI void sm_st(uint4* sm, uint32_t e, uint32_t E, const Fr& v) {
+    sm[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[E + e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
 // omega_N^e (or omega_N^-e) from the half table; `neg` = the value is the negative of the returned element
 KZG_DI Fr twiddle(const Fr* __restrict__ tw, uint32_t e, uint32_t log_n, uint32_t inverse, bool& neg) {
     const uint32_t mask = (log_n >= 32) ? 0xffffffffu : ((1u << log_n) - 1);
@@ -79,8 +94,7 @@ KZG_DI Fr twiddle(const Fr* __restrict__ tw, uint32_t e, uint32_t log_n, uint32_
 template <bool LAST>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
                                                                NttPassParams p, Fr minv) {
-    extern __shared__ uint4 ntt_smem_raw[];
-    Fr* sm = reinterpret_cast<Fr*>(ntt_smem_raw);
+    extern __shared__ uint4 sm[];
     const uint32_t tid = threadIdx.x;
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t;
     const uint32_t E = R * T;
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t d = e >> p.log_t, tl = e & (T - 1);
             uint32_t dr = __brev(d) >> (32 - p.log_r);
             if (p.log_r == 0) dr = 0;
-            sts_fr(&sm[(dr << p.log_t) + tl], lds_fr(&in[base + ((uint64_t)d << p.log_s) + tl]));
+            sm_st(sm, (dr << p.log_t) + tl, E, lds_fr(&in[base + ((uint64_t)d << p.log_s) + tl]));
         }
     } else {
         if (p.npass > 1) {
@@ -113,7 +127,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t t = e >> p.log_r, d = e & (R - 1);
             uint32_t dr = p.log_r ? (__brev(d) >> (32 - p.log_r)) : 0;
             uint64_t addr = (p.npass > 1) ? (((k10 + t) << log_s1) + (k2 << p.log_r) + d) : d;
-            sts_fr(&sm[(dr << p.log_t) + t], lds_fr(&in[addr]));
+            sm_st(sm, (dr << p.log_t) + t, E, lds_fr(&in[addr]));
         }
     }
     __syncthreads();
@@ -125,10 +139,10 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t tl = b & (T - 1), bb = b >> p.log_t;
             uint32_t i0 = ((bb << 1) << p.log_t) + tl;   // m = 1: pairs (2bb, 2bb+1), twiddle 1
             uint32_t i1 = i0 + T;
-            Fr u = lds_fr(&sm[i0]);
-            Fr t = lds_fr(&sm[i1]);
-            sts_fr(&sm[i0], u + t);
-            sts_fr(&sm[i1], u - t);
+            Fr u = sm_ld(sm, i0, E);
+            Fr t = sm_ld(sm, i1, E);
+            sm_st(sm, i0, E, u + t);
+            sm_st(sm, i1, E, u - t);
         }
         __syncthreads();
         s = 1;
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t k = (gg >> s) << (s + 2);
             uint32_t i0 = ((k + j) << p.log_t) + tl;
             uint32_t st = m << p.log_t;
-            Fr x0 = lds_fr(&sm[i0]), x1 = lds_fr(&sm[i0 + st]), x2 = lds_fr(&sm[i0 + 2 * st]), x3 = lds_fr(&sm[i0 + 3 * st]);
+            Fr x0 = sm_ld(sm, i0, E), x1 = sm_ld(sm, i0 + st, E), x2 = sm_ld(sm, i0 + 2 * st, E), x3 = sm_ld(sm, i0 + 3 * st, E);
             // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m)
             {
                 bool neg = false;
@@ -168,17 +182,17 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
                 Fr d = x1 + x3, e = x1 - x3;
                 x1 = neg2 ? e : d; x3 = neg2 ? d : e;
             }
-            sts_fr(&sm[i0], x0);
-            sts_fr(&sm[i0 + st], x1);
-            sts_fr(&sm[i0 + 2 * st], x2);
-            sts_fr(&sm[i0 + 3 * st], x3);
+            sm_st(sm, i0, E, x0);
+            sm_st(sm, i0 + st, E, x1);
+            sm_st(sm, i0 + 2 * st, E, x2);
+            sm_st(sm, i0 + 3 * st, E, x3);
         }
         __syncthreads();
     }
     if (!LAST) {
         for (uint32_t e = tid; e < E; e += NTT_THREADS) {
             uint32_t kj = e >> p.log_t, tl = e & (T - 1);
-            Fr v = lds_fr(&sm[e]);
+            Fr v = sm_ld(sm, e, E);
             uint64_t ex = ((uint64_t)kj * (p.low_offset + low0 + tl)) << p.tw_shift;
             if (ex != 0) {
                 bool neg;
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
     } else {
         for (uint32_t e = tid; e < E; e += NTT_THREADS) {
             uint32_t kp = e >> p.log_t, t = e & (T - 1);
-            Fr v = lds_fr(&sm[e]);
+            Fr v = sm_ld(sm, e, E);
             if (p.apply_scale) v = v * minv;
             uint64_t idx = (p.npass > 1)
                                ? ((k10 + t) + (k2 << p.log_r1) + ((uint64_t)kp << (p.log_n - p.log_r)))
