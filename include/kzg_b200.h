@@ -96,6 +96,11 @@ KZGB_API int kzgb_srs_read_affine(const kzgb_srs* srs, size_t start, size_t coun
 KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, size_t first, size_t count,
                                int window_bits, kzgb_srs** out);
 
+/* Lagrange-basis SRS from a monomial SRS WITHOUT the secret: the points eval_form.rs:254-280
+ * `compute_lagrange_basis(params)` returns (O(d^3) there), computed as an inverse NTT over the group:
+ * out[i] = (1/d) sum_j omega^(-ij) gs[j] = L_i(s)*G, natural omega^i order, d = 2^log_d <= size of `monomial`. */
+KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* monomial, uint32_t log_d, int window_bits, kzgb_srs** out);
+
 /* ---- G1 MSM: replaces G1Projective::multi_exp(gs[..m], scalars) ---------------
  * reference call sites: coeff_form.rs:61 (commit), :78 (create_witness), :102 (create_witness_batched),
  * eval_form.rs:118 (commit), :136 (create_witness).  Uses the first m points of the SRS (m <= n), as the

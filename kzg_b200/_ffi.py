@@ -327,3 +327,10 @@ def ntt_batch_dev(d_inout: int, d_tmp: int, log_n: int, batch: int, inverse: boo
     sc = None if scale is None else u64(scale, (4,))
     return check(lib().kzgb_ntt_batch_dev(C.c_void_p(d_inout), C.c_void_p(d_tmp), C.c_uint32(log_n), C.c_uint32(batch),
                                           C.c_int(int(inverse)), ptr(sc), C.c_void_p(stream)))
+
+
+def srs_lagrange_from_monomial(mono: SRS, log_d: int, window_bits: int = 0) -> SRS:
+    """Secret-free Lagrange-basis SRS (eval_form.rs:254-280) as a group inverse NTT of the monomial SRS."""
+    h = C.c_void_p()
+    check(lib().kzgb_srs_lagrange_from_monomial(mono._h, C.c_uint32(log_d), C.c_int(window_bits), C.byref(h)))
+    return SRS(h)

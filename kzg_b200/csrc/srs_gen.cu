@@ -13,6 +13,7 @@
 #include "ec.cuh"
 #include "msm.cuh"
 #include "fr_util.cuh"
+#include "ntt.cuh"
 
 namespace kzg {
 
@@ -164,6 +165,67 @@ __global__ void __launch_bounds__(128) xyzz_to_affine_batch_kernel(const XYZZ* _
     }
 }
 
+
+// --------------------------------------------------------------------------
+// Secret-free Lagrange-basis SRS: the points `compute_lagrange_basis(params)` derives from the monomial SRS alone
+// (eval_form.rs:254-280; O(d^3) there).  L_i(X) = (1/d) sum_j w^(-ij) X^j, hence
+//     L_i(s) * G = (1/d) * sum_j w^(-ij) * gs[j]  =  inverse NTT of the vector gs OVER THE GROUP:
+// radix-2 DIT butterflies (a, b) -> (a + w*b, a - w*b) on XYZZ points, w*b a variable-base scalar multiplication by a
+// power of omega^-1, then a final multiplication by d^-1 and a batched conversion to affine.
+// --------------------------------------------------------------------------
+KZG_DI XYZZ xyzz_scalar_mul(const XYZZ& p, const Fr& k_canonical) {
+    XYZZ acc = XYZZ::inf();
+    bool started = false;
+#pragma unroll 1
+    for (int i = 254; i >= 0; i--) {
+        uint32_t limb = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) limb = (j == (i >> 5)) ? k_canonical.l[j] : limb;
+        bool bit = (limb >> (i & 31)) & 1;
+        if (started) acc = xyzz_dbl(acc);
+        if (bit) { xyzz_add(acc, p); started = true; }
+    }
+    return acc;
+}
+
+__global__ void group_bitrev_load_kernel(const Affine* __restrict__ in, XYZZ* __restrict__ out, uint32_t log_d) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << log_d)) return;
+    uint32_t r = log_d ? (__brev(i) >> (32 - log_d)) : 0;
+    st_xyzz(&out[r], XYZZ::from_affine(ldg_affine(&in[i])));
+}
+
+// one DIT stage with half-size m = 2^s; tw[e] = omega^e (e < d/2), inverse twiddle omega^-e = -omega^(d/2 - e)
+__global__ void __launch_bounds__(128) group_ntt_stage_kernel(XYZZ* __restrict__ a, uint32_t log_d, uint32_t s,
+                                                              const Fr* __restrict__ tw) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t half_d = 1u << (log_d - 1);
+    if (b >= half_d) return;
+    const uint32_t m = 1u << s;
+    uint32_t j = b & (m - 1);
+    uint32_t k = (b >> s) << (s + 1);
+    XYZZ u = ld_xyzz(&a[k + j]);
+    XYZZ t = ld_xyzz(&a[k + j + m]);
+    if (j != 0) {
+        uint32_t e = j << (log_d - s - 1);            // exponent of omega; inverse: omega^-e = -omega^(d/2 - e)
+        Fr w = tw[half_d - e].from_mont();
+        t = xyzz_scalar_mul(t, w);
+        t.y = t.y.neg();
+    }
+    XYZZ hi = u, lo = u;
+    xyzz_add(hi, t);
+    t.y = t.y.neg();
+    xyzz_add(lo, t);
+    st_xyzz(&a[k + j], hi);
+    st_xyzz(&a[k + j + m], lo);
+}
+
+__global__ void __launch_bounds__(128) group_scale_kernel(XYZZ* __restrict__ a, uint32_t d, Fr k_canonical) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    st_xyzz(&a[i], xyzz_scalar_mul(ld_xyzz(&a[i]), k_canonical));
+}
+
 // scalars (device, Montgomery Fr) -> scalars[i] * G as affine points
 static int fixed_base_mul(const Fr* d_scalars, size_t n, Affine* d_out, cudaStream_t stream) {
     Affine* table = nullptr;
@@ -259,6 +321,58 @@ KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, si
     cudaFree(d_sc);
     if (!st) st = srs_build_table(h, c.stream);
     if (!st && (e = cudaStreamSynchronize(c.stream)) != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__);
+    if (st) { srs_free(h); return st; }
+    *out = h;
+    return KZGB_OK;
+}
+
+// Lagrange-basis SRS from a monomial SRS, without the secret (eval_form.rs:254-280 `compute_lagrange_basis`):
+// out[i] = L_i(s)*G for the size-2^log_d domain, natural omega^i order, from mono.gs[0 .. 2^log_d).
+KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* mono, uint32_t log_d, int window_bits, kzgb_srs** out) {
+    KZG_REQUIRE_INIT();
+    Context& c = ctx();
+    std::lock_guard<std::recursive_mutex> g(c.mu);
+    use_stream(c.stream);
+    if (!mono || !out) { set_error("kzgb_srs_lagrange_from_monomial: null argument"); return KZGB_ERR_INVALID_ARG; }
+    if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
+    const size_t d = (size_t)1 << log_d;
+    if (d > mono->n) {
+        set_error("kzgb_srs_lagrange_from_monomial: domain 2^%u larger than the SRS (%zu points)", log_d, mono->n);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    kzgb_srs* h = nullptr;
+    int st = srs_alloc(&h, d, window_bits);
+    if (st) return st;
+    XYZZ* work = nullptr;
+    cudaError_t e = cudaMalloc((void**)&work, d * sizeof(XYZZ));
+    if (e != cudaSuccess) { srs_free(h); return cuda_fail(e, "cudaMalloc(group ntt)", __FILE__, __LINE__); }
+    do {
+        group_bitrev_load_kernel<<<div_up(d, 256), 256, 0, c.stream>>>(mono->table, work, log_d);
+        c.launches++;
+        if (log_d > 0) {
+            const Fr* tw = nullptr;
+            if ((st = ntt_get_twiddles(log_d, c.stream, &tw))) break;
+            for (uint32_t s = 0; s < log_d; s++) {
+                group_ntt_stage_kernel<<<div_up(d / 2, 128), 128, 0, c.stream>>>(work, log_d, s, tw);
+                c.launches++;
+            }
+            FrHost dinv = fr_host_inv(fr_host_from_u64((uint64_t)d));
+            FrHost one_canon;
+            memset(one_canon.l, 0, 32);
+            one_canon.l[0] = 1;
+            FrHost dinv_canon = fr_host_mul(dinv, one_canon);   // out of Montgomery form
+            Fr k;
+            memcpy(k.l, dinv_canon.l, 32);
+            group_scale_kernel<<<div_up(d, 128), 128, 0, c.stream>>>(work, (uint32_t)d, k);
+            c.launches++;
+        }
+        xyzz_to_affine_batch_kernel<<<div_up((d + NORM_BATCH - 1) / NORM_BATCH, 128), 128, 0, c.stream>>>(work, h->table, d);
+        c.launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) { st = cuda_fail(e, "group ntt launch", __FILE__, __LINE__); break; }
+        if ((st = srs_build_table(h, c.stream))) break;
+        if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) st = cuda_fail(e, "group ntt", __FILE__, __LINE__);
+    } while (0);
+    cudaFree(work);
     if (st) { srs_free(h); return st; }
     *out = h;
     return KZGB_OK;

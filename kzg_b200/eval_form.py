@@ -18,6 +18,17 @@ def compute_lagrange_basis_known_secret(s, d: int, window_bits: int = 0) -> _ffi
     return _ffi.srs_generate(1, s, d, window_bits=window_bits)
 
 
+def compute_lagrange_basis(params: KZGParams, window_bits: int = 0) -> _ffi.SRS:
+    """eval_form.rs:254-280 `compute_lagrange_basis(params)` (G1 half): the Lagrange-basis SRS derived from the
+    monomial SRS alone -- no secret needed.  The reference builds it in O(d^3) from Lagrange polynomials and MSMs;
+    here it is the inverse NTT of `gs` over the group, L_i(s)*G = (1/d) sum_j omega^(-ij) gs[j].  `len(params)` must be
+    a power of two (the reference asserts d == gs.len(), eval_form.rs:256)."""
+    d = len(params)
+    m, exp, _ = compute_omega(d)
+    assert m == d, "assertion failed: d == params.gs.len()"
+    return _ffi.srs_lagrange_from_monomial(params.srs, exp, window_bits)
+
+
 def div_by_omega_i(evals: EvaluationDomain, m: int) -> EvaluationDomain:
     """eval_form.rs:58-84 applied to `evals - evals[m]` (as create_witness does, :125-131)."""
     if len(evals.coeffs) == 1:

@@ -156,3 +156,22 @@ def test_eval_form_prover(golden):
     assert not prover.create_witness_all().any()
     with pytest.raises(AssertionError):                               # eval_form.rs:115
         prover.commit(kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values[:8])))
+
+
+@pytest.mark.parametrize("d", [1, 2, 16, 64, 1024])
+def test_compute_lagrange_basis_without_the_secret(gpu, d):
+    """eval_form.rs:254-280: the Lagrange SRS derived from params.gs alone (group inverse NTT) equals the closed form
+    L_i(s)*G under the known secret, point for point; and an eval-form commitment over it equals the monomial one."""
+    params = kzg.setup(SECRET, d)
+    lagrange = kzg.compute_lagrange_basis(params)
+    if d > 1:
+        expect = kzg.compute_lagrange_basis_known_secret(SECRET, d)
+        assert (lagrange.read_affine() == expect.read_affine()).all()
+    else:
+        assert (lagrange.read_affine() == params.gs_affine()).all()     # L_0 = 1
+    values = O.fr_stream(42, d)
+    evals = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values))
+    prover = kzg.KZGProverEvalForm(params, lagrange)
+    coeffs = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values))
+    coeffs.ifft()
+    assert (prover.commit(evals) == kzg.KZGProver(params).commit(coeffs.into_polynomial())).all()
