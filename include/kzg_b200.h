@@ -179,6 +179,17 @@ KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t wor
 KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint32_t batch, int inverse,
                                 const kzgb_fr* scale, void* stream);
 
+/* ---- EvaluationDomain helpers off the prover path: element-wise passes and the coset transforms.
+ * op 0: a[i] *= b[i]  (mul_assign, ft.rs:220-244)      op 1: a[i] -= b[i]  (sub_assign, ft.rs:247-271)
+ * op 2: a[i] *= k^i   (distribute_powers, ft.rs:142-166)  op 3: a[i] *= k (e.g. divide_by_z_on_coset, ft.rs:192-217) */
+KZGB_API int kzgb_fr_vec_op(int op, kzgb_fr* a, const kzgb_fr* b, size_t n, const kzgb_fr* k);
+KZGB_API int kzgb_fr_vec_op_dev(int op, void* d_a, const void* d_b, size_t n, const kzgb_fr* k, void* stream);
+/* coset_fft (ft.rs:168-171: distribute_powers(7) then fft) / icoset_fft (ft.rs:173-178: ifft then distribute_powers(7^-1)) */
+KZGB_API int kzgb_coset_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse);
+/* transform pipeline of Polynomial::fft_mul (polynomial.rs:167-183): pad to m = 2^k >= na + nb, fft, multiply, ifft */
+KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t nb, kzgb_fr* out, size_t out_capacity,
+                           size_t* m_out);
+
 /* ---- synthetic inputs: splitmix64 Fr stream, Montgomery form, on the device ----
  * element i of stream `seed` = 4 consecutive outputs as a 256-bit LE integer mod r (mode 0), or a single
  * u64 (mode 1, the distribution of benches/commit_coeff_form.rs:16-20). */

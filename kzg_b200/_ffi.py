@@ -334,3 +334,30 @@ def srs_lagrange_from_monomial(mono: SRS, log_d: int, window_bits: int = 0) -> S
     h = C.c_void_p()
     check(lib().kzgb_srs_lagrange_from_monomial(mono._h, C.c_uint32(log_d), C.c_int(window_bits), C.byref(h)))
     return SRS(h)
+
+
+def fr_vec_op(op: int, a, b=None, k=None) -> np.ndarray:
+    """op 0: a*b, 1: a-b, 2: a[i]*k^i, 3: a*k on host vectors (returns a new array)."""
+    a = u64(a, (-1, 4)).copy()
+    bb = None if b is None else u64(b, (-1, 4))
+    kk = None if k is None else u64(k, (4,))
+    check(lib().kzgb_fr_vec_op(C.c_int(op), ptr(a), ptr(bb), C.c_size_t(len(a)), ptr(kk)))
+    return a
+
+
+def coset_ntt(a, log_n: int, inverse: bool = False):
+    a = u64(a, (-1, 4)).copy()
+    st = check(lib().kzgb_coset_ntt_fr(ptr(a), C.c_uint32(log_n), C.c_int(int(inverse))))
+    return st, a
+
+
+def poly_mul(a, b) -> np.ndarray:
+    """fft_mul pipeline: returns all m = 2^k >= len(a)+len(b) coefficients of a*b."""
+    a, b = u64(a, (-1, 4)), u64(b, (-1, 4))
+    m = 1
+    while m < len(a) + len(b):
+        m *= 2
+    out = np.zeros((m, 4), dtype=np.uint64)
+    mo = C.c_size_t(0)
+    check(lib().kzgb_poly_mul(ptr(a), C.c_size_t(len(a)), ptr(b), C.c_size_t(len(b)), ptr(out), C.c_size_t(m), C.byref(mo)))
+    return out[: mo.value]

@@ -105,6 +105,11 @@ struct Fe {
         for (int i = 0; i < N; i++) r.l[i] = 0;
         return r;
     }
+    __host__ static Fe zero_host() {
+        Fe r;
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
     KZG_DI static Fe one() {
         Fe r;
 #pragma unroll

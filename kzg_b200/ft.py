@@ -72,6 +72,40 @@ class EvaluationDomain:
             raise PolynomialDegreeTooLarge()
         self.coeffs = out
 
+    # ---- helpers off the prover path (ft.rs:142-271) ----
+    def distribute_powers(self, g: int) -> None:
+        # ft.rs:142-166: coeffs[i] *= g^i
+        self.coeffs = _ffi.fr_vec_op(2, self.coeffs, None, fr(g))
+
+    def coset_fft(self) -> None:
+        # ft.rs:168-171
+        self._check()
+        self.coeffs = _ffi.coset_ntt(self.coeffs, self.exp, False)[1]
+
+    def icoset_fft(self) -> None:
+        # ft.rs:173-178
+        self._check()
+        self.coeffs = _ffi.coset_ntt(self.coeffs, self.exp, True)[1]
+
+    def z(self, tau: int) -> int:
+        # ft.rs:182-187: tau^m - 1
+        return (pow(tau, len(self.coeffs), R_MOD) - 1) % R_MOD
+
+    def divide_by_z_on_coset(self) -> None:
+        # ft.rs:192-217: multiply by z(7)^-1
+        i = pow(self.z(7), -1, R_MOD)
+        self.coeffs = _ffi.fr_vec_op(3, self.coeffs, None, fr(i))
+
+    def mul_assign(self, other: "EvaluationDomain") -> None:
+        # ft.rs:220-244
+        assert len(self.coeffs) == len(other.coeffs)
+        self.coeffs = _ffi.fr_vec_op(0, self.coeffs, other.coeffs)
+
+    def sub_assign(self, other: "EvaluationDomain") -> None:
+        # ft.rs:247-271
+        assert len(self.coeffs) == len(other.coeffs)
+        self.coeffs = _ffi.fr_vec_op(1, self.coeffs, other.coeffs)
+
     def into_polynomial(self) -> Polynomial:
         # From<EvaluationDomain> for Polynomial, ft.rs:27-31
         return Polynomial.new(self.coeffs)

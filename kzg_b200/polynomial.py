@@ -96,6 +96,27 @@ class Polynomial:
         r.coeffs[0] = fr_sub(r.coeffs[0], y)
         return r
 
+    # ---- multiplication (off the prover path; polynomial.rs:167-191, 473-487) ----
+    FFT_MUL_THRESHOLD = 128  # polynomial.rs:13
+
+    def fft_mul(self, other: "Polynomial") -> "Polynomial":
+        """polynomial.rs:167-183: operands padded to 2^k >= n + k coefficients, fft, pointwise product, ifft; the
+        result keeps all 2^k coefficients and its degree is re-measured (Polynomial::new)."""
+        return Polynomial.new(_ffi.poly_mul(self.slice_coeffs(), other.slice_coeffs()))
+
+    def mul(self, other: "Polynomial") -> "Polynomial":
+        """Mul for Polynomial (polynomial.rs:473-487): degree+degree+1 coefficients, declared degree = the sum
+        (not shrunk).  Same coefficients as the schoolbook loop, computed through the transform pipeline."""
+        full = _ffi.poly_mul(self.slice_coeffs(), other.slice_coeffs())
+        deg = self.degree + other.degree
+        return Polynomial(full[: deg + 1].copy(), deg)
+
+    def best_mul(self, other: "Polynomial") -> "Polynomial":
+        # polynomial.rs:185-191
+        if self.degree < self.FFT_MUL_THRESHOLD or other.degree < self.FFT_MUL_THRESHOLD:
+            return self.mul(other)
+        return self.fft_mul(other)
+
     @staticmethod
     def lagrange_interpolation(xs, ys) -> "Polynomial":
         """polynomial.rs:237-293.  One point gives X + (y - x) (degree 1) exactly as the reference does

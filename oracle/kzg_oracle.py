@@ -439,6 +439,34 @@ class EvaluationDomain:
         serial_fft(self.coeffs, self.omegainv, self.exp)
         self.coeffs = [v * self.minv % R_MOD for v in self.coeffs]
 
+    def distribute_powers(self, g: int):
+        # ft.rs:142-166: coeffs[i] *= g^i
+        self.coeffs = [v * pow(g, i, R_MOD) % R_MOD for i, v in enumerate(self.coeffs)]
+
+    def coset_fft(self):
+        # ft.rs:168-171
+        self.distribute_powers(FR_GENERATOR)
+        self.fft()
+
+    def icoset_fft(self):
+        # ft.rs:173-178
+        self.ifft()
+        self.distribute_powers(self.geninv)
+
+    def z(self, tau: int) -> int:
+        # ft.rs:182-187
+        return (pow(tau, len(self.coeffs), R_MOD) - 1) % R_MOD
+
+    def divide_by_z_on_coset(self):
+        # ft.rs:192-217
+        i = pow(self.z(FR_GENERATOR), -1, R_MOD)
+        self.coeffs = [v * i % R_MOD for v in self.coeffs]
+
+    def sub_assign(self, other: "EvaluationDomain"):
+        # ft.rs:247-271
+        assert len(self.coeffs) == len(other.coeffs)
+        self.coeffs = [(a - b) % R_MOD for a, b in zip(self.coeffs, other.coeffs)]
+
     def mul_assign(self, other: "EvaluationDomain"):
         # ft.rs:220-244
         assert len(self.coeffs) == len(other.coeffs)

@@ -175,3 +175,42 @@ def test_compute_lagrange_basis_without_the_secret(gpu, d):
     coeffs = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(values))
     coeffs.ifft()
     assert (prover.commit(evals) == kzg.KZGProver(params).commit(coeffs.into_polynomial())).all()
+
+
+def test_coset_and_pointwise_helpers(gpu):
+    """ft.rs:142-271 on the device vs the oracle restatement, incl. the quotient-on-a-coset pipeline."""
+    n = 1 << 10
+    a_i, b_i = O.fr_stream(2, n // 2), O.fr_stream(3, n // 2)
+    prod = O.Polynomial.new(a_i).fft_mul(O.Polynomial.new(b_i)).coeffs + [0] * (2 * n)
+    c_i = [(prod[i] + prod[i + n]) % R for i in range(n)]
+    pad = lambda v: scalar.fr_vec(v + [0] * (n - len(v)))
+    A, B, C = (kzg.EvaluationDomain.from_coeffs(pad(v)) for v in (a_i, b_i, c_i))
+    oa = O.EvaluationDomain.from_coeffs(a_i + [0] * (n - len(a_i)))
+    oa.coset_fft()
+    for dom in (A, B, C):
+        dom.coset_fft()
+    assert scalar.fr_vec_int(A.coeffs) == oa.coeffs
+    A.mul_assign(B)
+    A.sub_assign(C)
+    A.divide_by_z_on_coset()
+    A.icoset_fft()
+    assert scalar.fr_vec_int(A.coeffs) == [prod[i + n] for i in range(n)]
+    d = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(a_i))
+    d.distribute_powers(5)
+    assert scalar.fr_vec_int(d.coeffs) == [v * pow(5, i, R) % R for i, v in enumerate(a_i)]
+    assert d.z(7) == (pow(7, n // 2, R) - 1) % R
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (50, 50), (129, 130), (1000, 3000)])
+def test_polynomial_mul(gpu, n, k):
+    """ft.rs:411-434 polynomial_arith (fft_mul == naive mul) and the best_mul switch (polynomial.rs:185-191)."""
+    a_i, b_i = O.fr_stream(1, n), O.fr_stream(2, k)
+    a, b = kzg.Polynomial.from_ints(a_i), kzg.Polynomial.from_ints(b_i)
+    oa, ob = O.Polynomial.new(a_i), O.Polynomial.new(b_i)
+    ref = oa.best_mul(ob)
+    got = a.best_mul(b)
+    assert got.degree == ref.degree and len(got.coeffs) == len(ref.coeffs)
+    assert scalar.fr_vec_int(got.coeffs) == ref.coeffs
+    if n <= 129:
+        naive = oa.mul_naive(ob)
+        assert scalar.fr_vec_int(a.mul(b).coeffs) == naive.coeffs and a.mul(b).degree == naive.degree
