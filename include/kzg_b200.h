@@ -190,6 +190,15 @@ KZGB_API int kzgb_coset_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse);
 KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t nb, kzgb_fr* out, size_t out_capacity,
                            size_t* m_out);
 
+/* ---- wire / disk encodings: ZCash/IETF compressed G1 (48 B; blstrs to_compressed /
+ * from_compressed_unchecked: on-curve checked, subgroup membership not) and canonical little-endian Fr
+ * (blstrs to_bytes_le / from_bytes_le).  The reference's own serde support is dead code (lib.rs:13, ft.rs:389-404). */
+KZGB_API int kzgb_g1_compress(const kzgb_p1_affine* points, size_t n, uint8_t* out48);
+KZGB_API int kzgb_g1_decompress(const uint8_t* in48, size_t n, kzgb_p1_affine* out);
+KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out);
+KZGB_API int kzgb_srs_export_compressed(const kzgb_srs* srs, size_t start, size_t count, uint8_t* out48);
+KZGB_API int kzgb_fr_bytes_le(const void* in, void* out, size_t n, int to_bytes);
+
 /* ---- synthetic inputs: splitmix64 Fr stream, Montgomery form, on the device ----
  * element i of stream `seed` = 4 consecutive outputs as a 256-bit LE integer mod r (mode 0), or a single
  * u64 (mode 1, the distribution of benches/commit_coeff_form.rs:16-20). */

@@ -361,3 +361,51 @@ def poly_mul(a, b) -> np.ndarray:
     mo = C.c_size_t(0)
     check(lib().kzgb_poly_mul(ptr(a), C.c_size_t(len(a)), ptr(b), C.c_size_t(len(b)), ptr(out), C.c_size_t(m), C.byref(mo)))
     return out[: mo.value]
+
+
+# ---------------------------------------------------------------------------
+# wire formats
+# ---------------------------------------------------------------------------
+def g1_compress(points) -> bytes:
+    pts = u64(points, (-1, 12))
+    out = np.zeros(48 * len(pts), dtype=np.uint8)
+    check(lib().kzgb_g1_compress(ptr(pts), C.c_size_t(len(pts)), ptr(out)))
+    return out.tobytes()
+
+
+def g1_decompress(data: bytes) -> np.ndarray:
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    assert len(buf) % 48 == 0
+    n = len(buf) // 48
+    out = np.zeros((n, 12), dtype=np.uint64)
+    check(lib().kzgb_g1_decompress(ptr(buf), C.c_size_t(n), ptr(out)))
+    return out
+
+
+def srs_from_compressed(data: bytes, window_bits: int = 0) -> SRS:
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    assert len(buf) % 48 == 0
+    h = C.c_void_p()
+    check(lib().kzgb_srs_create_g1_compressed(ptr(buf), C.c_size_t(len(buf) // 48), C.c_int(window_bits), C.byref(h)))
+    return SRS(h)
+
+
+def srs_export_compressed(srs: SRS, start: int = 0, count=None) -> bytes:
+    count = len(srs) - start if count is None else count
+    out = np.zeros(48 * count, dtype=np.uint8)
+    check(lib().kzgb_srs_export_compressed(srs._h, C.c_size_t(start), C.c_size_t(count), ptr(out)))
+    return out.tobytes()
+
+
+def fr_to_bytes_le(a) -> bytes:
+    a = u64(a, (-1, 4))
+    out = np.zeros_like(a)
+    check(lib().kzgb_fr_bytes_le(ptr(a), ptr(out), C.c_size_t(len(a)), C.c_int(1)))
+    return out.tobytes()
+
+
+def fr_from_bytes_le(data: bytes) -> np.ndarray:
+    a = np.frombuffer(data, dtype=np.uint64).reshape(-1, 4).copy()
+    out = np.zeros_like(a)
+    check(lib().kzgb_fr_bytes_le(ptr(a), ptr(out), C.c_size_t(len(a)), C.c_int(0)))
+    return out

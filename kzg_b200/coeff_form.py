@@ -62,3 +62,24 @@ class KZGProver:
         if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
             raise PointNotOnPolynomial()
         return KZGBatchWitness(Polynomial(r, len(r) - 1), w)
+
+
+class KZGVerifier:
+    """coeff_form.rs:43-45, 114-183 -- only the MSM-backed check is provided.  `verify_eval` and
+    `verify_eval_batched` need pairings and G2 arithmetic, which stay on the CPU side of an integration."""
+
+    def __init__(self, parameters: KZGParams):
+        self._parameters = parameters
+
+    def verify_poly(self, commitment, polynomial: Polynomial) -> bool:
+        # coeff_form.rs:119-124: recompute the commitment and compare
+        n = polynomial.num_coeffs()
+        if n > len(self._parameters):
+            raise IndexError(f"range end index {n} out of range for slice of length {len(self._parameters)}")
+        check = self._parameters.srs.msm(polynomial.slice_coeffs())
+        return bool((check == np.asarray(commitment, dtype=np.uint64).reshape(12)).all())
+
+    def verify_eval(self, *a, **k):
+        raise NotImplementedError("pairing-based verification (coeff_form.rs:126-142) is outside this library")
+
+    verify_eval_batched = verify_eval

@@ -532,6 +532,12 @@ struct Fe {
         }
         return v;
     }
+    KZG_DI static uint32_t mod_limb(int i) {  // run-time indexed limb of the modulus
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) v = (i == k) ? P::mod(k) : v;
+        return v;
+    }
     KZG_DI static uint32_t modm2_limb(int i) {
         uint32_t v = 0;
 #pragma unroll

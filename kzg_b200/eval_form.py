@@ -71,3 +71,17 @@ class KZGProverEvalForm:
     def create_witness_all(self) -> np.ndarray:
         # eval_form.rs:142-146: identity * 0
         return G1_IDENTITY_AFFINE.copy()
+
+
+class KZGVerifierEvalForm:
+    """eval_form.rs:149-219 -- verify_poly only (iFFT + monomial MSM, :162-171); the pairing checks are out of scope."""
+
+    def __init__(self, parameters: KZGParams):
+        self._parameters = parameters
+
+    def verify_poly(self, commitment, evals: EvaluationDomain) -> bool:
+        coeffs = evals.clone_with_different_coeffs(evals.coeffs.copy())
+        coeffs.ifft()
+        p = coeffs.into_polynomial()
+        check = self._parameters.srs.msm(p.slice_coeffs())
+        return bool((check == np.asarray(commitment, dtype=np.uint64).reshape(12)).all())

@@ -47,6 +47,14 @@ class KZGParams:
     def from_g1_affine(cls, gs, window_bits: int = 0) -> "KZGParams":
         return cls(_ffi.SRS.from_affine(gs, window_bits))
 
+    @classmethod
+    def from_compressed(cls, data: bytes, window_bits: int = 0) -> "KZGParams":
+        """G1 powers from a ceremony-style file image: n x 48-byte compressed points (decompressed on the device)."""
+        return cls(_ffi.srs_from_compressed(data, window_bits))
+
+    def to_compressed(self) -> bytes:
+        return _ffi.srs_export_compressed(self._srs)
+
     def __len__(self) -> int:
         return len(self._srs)
 

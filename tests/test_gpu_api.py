@@ -214,3 +214,45 @@ def test_polynomial_mul(gpu, n, k):
     if n <= 129:
         naive = oa.mul_naive(ob)
         assert scalar.fr_vec_int(a.mul(b).coeffs) == naive.coeffs and a.mul(b).degree == naive.degree
+
+
+def test_verify_poly_and_wire_formats(gpu, params):
+    """coeff_form.rs:119-124 / eval_form.rs:162-171 verify_poly; compressed-G1 and LE-Fr encodings vs the oracle."""
+    prover, verifier = kzg.KZGProver(params), kzg.KZGVerifier(params)
+    coeffs = O.fr_stream(42, 12)
+    poly = kzg.Polynomial.from_ints(coeffs)
+    c = prover.commit(poly)
+    assert verifier.verify_poly(c, poly)
+    assert not verifier.verify_poly(c, kzg.Polynomial.from_ints(O.fr_stream(43, 12)))
+    evals = kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(O.fr_stream(42, 16)))
+    lag = kzg.compute_lagrange_basis(params)
+    ce = kzg.KZGProverEvalForm(params, lag).commit(evals)
+    assert kzg.KZGVerifierEvalForm(params).verify_poly(ce, evals)
+    # SRS export / import through 48-byte compressed points
+    blob = params.to_compressed()
+    expect = b"".join(O.g1_compress(O.g1_mul(O.G1_GENERATOR, pow(SECRET, i, R))) for i in range(len(params)))
+    assert blob == expect
+    again = kzg.KZGParams.from_compressed(blob)
+    assert (again.gs_affine() == params.gs_affine()).all()
+    assert (kzg.KZGProver(again).commit(poly) == c).all()
+    # identity, sign bit, and malformed encodings
+    pts = np.vstack([params.gs_affine(0, 3), np.zeros((1, 12), dtype=np.uint64)])
+    comp = gpu.g1_compress(pts)
+    assert comp[-48:] == bytes([0xC0]) + bytes(47)
+    assert (gpu.g1_decompress(comp) == pts).all()
+    neg = bytearray(comp[:48]); neg[0] ^= 0x20
+    xy, nxy = scalar.g1_affine_xy(pts[0]), scalar.g1_affine_xy(gpu.g1_decompress(bytes(neg))[0])
+    assert nxy == (xy[0], O.P_MOD - xy[1])
+    with pytest.raises(gpu.KZGBackendError):
+        gpu.g1_decompress(bytes([0x80]) + bytes(46) + bytes([1]))       # x = 1: 1 + 4 = 5 is not a square mod p?  or on-curve
+    with pytest.raises(gpu.KZGBackendError):
+        gpu.g1_decompress(bytes([0x9f]) + bytes([0xff]) * 47)             # x >= p
+    with pytest.raises(gpu.KZGBackendError):
+        gpu.g1_decompress(bytes(48))                                      # uncompressed flag clear
+    # Fr canonical little-endian bytes
+    vals = [0, 1, R - 1, SECRET]
+    b = gpu.fr_to_bytes_le(scalar.fr_vec(vals))
+    assert b == b"".join(O.fr_to_bytes_le(v) for v in vals)
+    assert (gpu.fr_from_bytes_le(b) == scalar.fr_vec(vals)).all()
+    with pytest.raises(gpu.KZGBackendError):
+        gpu.fr_from_bytes_le(R.to_bytes(32, "little"))                    # r itself is not canonical
