@@ -163,6 +163,9 @@ KZGB_API int kzgb_profile_enable(int on);
 KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts); /* arrays of kzgb_profile_stage_count() */
 KZGB_API int kzgb_profile_stage_count(void);
 KZGB_API const char* kzgb_profile_stage_name(int stage);
+/* per-launch trace (diagnostics): warm in-stream time of every kernel launch, keyed by the source line of the launch */
+KZGB_API int kzgb_trace_enable(int on);
+KZGB_API int kzgb_trace_read(int* lines, float* ms, int cap);
 
 /* ---- four-step building blocks of the multi-GPU NTT (N >= 2^24, one all-to-all; structural
  * precedent: parallel_fft, ft.rs:336-387).  View the vector as N1 x N2 (index i1*N2 + i2).  Rank g holds the slab

@@ -231,6 +231,18 @@ def profile_read() -> dict:
     return {l.kzgb_profile_stage_name(i).decode(): (sums[i], int(cnts[i])) for i in range(n) if cnts[i]}
 
 
+def trace_enable(on: bool = True) -> None:
+    check(lib().kzgb_trace_enable(C.c_int(int(on))))
+
+
+def trace_read(cap: int = 4096):
+    """[(source line of the launch, ms since the previous launch mark)] since trace_enable (synchronises)."""
+    lines = (C.c_int * cap)()
+    ms = (C.c_float * cap)()
+    n = check(lib().kzgb_trace_read(lines, ms, C.c_int(cap)))
+    return [(int(lines[i]), float(ms[i])) for i in range(n)]
+
+
 def ntt(a, log_n: int, inverse: bool = False) -> np.ndarray:
     """Host vector ([2^log_n,4] u64 Montgomery Fr) -> transformed copy.  Status 2 raises in the host mirror."""
     a = u64(a, (-1, 4)).copy()

@@ -115,9 +115,49 @@ void stage_end(int stage, cudaStream_t stream) {
     g_open[stage] = nullptr;
 }
 
+// ---- per-launch trace ----
+struct TraceRec { const char* file; int line; cudaEvent_t e; };
+static bool g_trace = false;
+static std::vector<TraceRec> g_trace_recs;
+void trace_mark(const char* file, int line) {
+    if (!g_trace) return;
+    Context& c = ctx();
+    cudaEvent_t e = get_event();
+    cudaEventRecord(e, c.have_last ? c.last_stream : c.stream);
+    g_trace_recs.push_back(TraceRec{file, line, e});
+}
+
 }  // namespace kzg
 
 using namespace kzg;
+
+// on = 1: start tracing (a first mark is recorded on the library stream); on = 0: stop
+extern "C" KZGB_API int kzgb_trace_enable(int on) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    g_trace = on != 0;
+    return KZGB_OK;
+}
+// Synchronises, then writes up to cap records: lines[i] = source line of the i-th KZG_LAUNCHED(), ms[i] = time since
+// the previous mark (0 for the first); returns the number of records (negative on error) and clears the trace.
+extern "C" KZGB_API int kzgb_trace_read(int* lines, float* ms, int cap) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_CUDA(cudaDeviceSynchronize());
+    int n = 0;
+    for (size_t i = 0; i < g_trace_recs.size(); i++) {
+        if (n < cap) {
+            float t = 0;
+            if (i > 0) cudaEventElapsedTime(&t, g_trace_recs[i - 1].e, g_trace_recs[i].e);
+            lines[n] = g_trace_recs[i].line;
+            ms[n] = t;
+            n++;
+        }
+        g_free_events.push_back(g_trace_recs[i].e);
+    }
+    g_trace_recs.clear();
+    return n;
+}
 
 extern "C" KZGB_API int kzgb_profile_enable(int on) {
     std::lock_guard<std::recursive_mutex> g(ctx().mu);

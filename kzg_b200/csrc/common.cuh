@@ -58,6 +58,7 @@ void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr
 #define KZG_LAUNCHED()                                                              \
     do {                                                                            \
         ::kzg::ctx().launches++;                                                    \
+        ::kzg::trace_mark(__FILE__, __LINE__);                                      \
         KZG_CUDA(cudaGetLastError());                                               \
     } while (0)
 
@@ -68,6 +69,9 @@ enum Stage {
     ST_NTT, ST_SCAN, ST_DIV_OMEGA, ST_INTERP, ST_BATCH_DIV, ST_COUNT
 };
 void stage_begin(int stage, cudaStream_t stream);
+// per-launch trace (diagnostics): when enabled, every KZG_LAUNCHED() records an event on the call's stream, so the
+// warm, in-stream duration of each kernel of a pipeline can be read back (ncu launch lists are cold and serialised)
+void trace_mark(const char* file, int line);
 void stage_end(int stage, cudaStream_t stream);
 struct StageScope {
     int stage; cudaStream_t stream;

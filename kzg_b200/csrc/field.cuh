@@ -279,6 +279,102 @@ struct Fe {
         r.final_sub();
         return r;
     }
+
+    // ------------------------------------------------------------------------------------------------------
+    // FP64-pipe product (B200 has a full-rate DFMA pipe, 64 lanes/clk/SM, separate from the FMA-heavy pipe that
+    // executes IMAD.WIDE).  a is taken as N 32-bit limbs, b as 2N 16-bit chunks; every partial product is
+    // < 2^48 and a column of <= 12 of them plus its bias stays below 2^52, so a chain of DFMAs accumulates each
+    // column EXACTLY in the mantissa of a double biased by 2^52.  Column j (weight 2^(32j)) has an "E" sum over
+    // the low chunks and an "O" sum over the high chunks (weight 2^(32j+16)).  The raw bit patterns
+    // 0x433<<52 | sum are then added as 64-bit integers at limb j; the exponent bits that come along are
+    // cancelled by constants folded into the biases (limbs of -C mod 2^(64N), C = the sum of all exponent
+    // patterns), so no masking is needed.  2*N*N DFMAs + 4N-2 integer adds + 2N funnel shifts replace the
+    // N*N wide multiply-adds of the schoolbook product; the Montgomery reduction stays on the IMAD pipe.
+    // Model and bounds: scripts/dfma_model.py.
+    // ------------------------------------------------------------------------------------------------------
+    KZG_DI static double dfma_bias_e(int j) {
+        // 2^52 + limb j of -C
+        return __hiloint2double(0x43300000, j == 0 ? 0u : (j == 1 ? 0xBCD00000u : 0xBCCFBCCFu));
+    }
+    KZG_DI static void mul_wide_dfma(uint32_t* T, const Fe& a, const Fe& b) {
+        constexpr int M = 2 * N;
+        const double two52 = __hiloint2double(0x43300000, 0);
+        double ad[N], bl[N], bh[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            ad[i] = __hiloint2double(0x43300000, a.l[i]) - two52;
+            bl[i] = __hiloint2double(0x43300000, b.l[i] & 0xffffu) - two52;
+            bh[i] = __hiloint2double(0x43300000, b.l[i] >> 16) - two52;
+        }
+        uint32_t Elo[M - 1], Ehi[M - 1], Olo[M - 1], Ohi[M - 1];
+#pragma unroll
+        for (int j = 0; j < M - 1; j++) {
+            double e = dfma_bias_e(j);
+            // last O column also carries limb 2N-1 of -C (shifted into its own 2^16 frame)
+            double o = (j == M - 2) ? __hiloint2double(0x43300000 | 0xBCCFu, 0xBCCF0000u) : two52;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const int k = j - i;
+                if (k >= 0 && k < N) {
+                    e = __fma_rn(ad[i], bl[k], e);
+                    o = __fma_rn(ad[i], bh[k], o);
+                }
+            }
+            Elo[j] = (uint32_t)__double2loint(e); Ehi[j] = (uint32_t)__double2hiint(e);
+            Olo[j] = (uint32_t)__double2loint(o); Ohi[j] = (uint32_t)__double2hiint(o);
+        }
+        uint32_t S1[M], S2[M];
+        S1[0] = Elo[0];
+        S1[1] = add_cc(Elo[1], Ehi[0]);
+#pragma unroll
+        for (int k = 2; k < M - 1; k++) S1[k] = addc_cc(Elo[k], Ehi[k - 1]);
+        S1[M - 1] = addc(Ehi[M - 2], 0);
+        S2[0] = Olo[0];
+        S2[1] = add_cc(Olo[1], Ohi[0]);
+#pragma unroll
+        for (int k = 2; k < M - 1; k++) S2[k] = addc_cc(Olo[k], Ohi[k - 1]);
+        S2[M - 1] = addc(Ohi[M - 2], 0);
+        T[0] = add_cc(S1[0], S2[0] << 16);
+#pragma unroll
+        for (int k = 1; k < M - 1; k++) T[k] = addc_cc(S1[k], __funnelshift_l(S2[k - 1], S2[k], 16));
+        T[M - 1] = addc(S1[M - 1], __funnelshift_l(S2[M - 2], S2[M - 1], 16));
+    }
+    // T (2N limbs, < MOD * 2^(32N)) -> T / 2^(32N) mod MOD: word-serial reduction on the interleaved (E, O) frame.
+    KZG_DI static Fe mont_reduce_wide(const uint32_t* T) {
+        uint32_t E[N], O[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { E[j] = T[j]; O[j] = 0; }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            reduce_step(E, O);
+            // frame >>= 32: new E = O + (old E[1] at limb 0), new O = old E >> 64; then add T[N+i] at limb N-1
+            uint32_t nE[N], nO[N];
+            nE[0] = add_cc(O[0], E[1]);
+#pragma unroll
+            for (int j = 1; j < N - 1; j++) nE[j] = addc_cc(O[j], 0);
+            nE[N - 1] = addc_cc(O[N - 1], T[N + i]);
+            uint32_t top = addc(0, 0);
+#pragma unroll
+            for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
+            nO[N - 2] = 0;
+            nO[N - 1] = top;   // carry out of limb N-1 has weight 2^(32N) = O[N-1]
+#pragma unroll
+            for (int j = 0; j < N; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+        }
+        Fe r;
+        r.l[0] = E[0];
+        r.l[1] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int j = 2; j < N; j++) r.l[j] = addc_cc(E[j], O[j - 1]);
+        r.final_sub();
+        return r;
+    }
+    KZG_DI static Fe mul_dfma(const Fe& a, const Fe& b) {
+        uint32_t T[2 * N];
+        mul_wide_dfma(T, a, b);
+        return mont_reduce_wide(T);
+    }
+    __device__ __noinline__ static Fe mul_dfma_outlined(Fe a, Fe b) { return mul_dfma(a, b); }
     KZG_DI Fe sqr() const {
 #ifdef KZG_FQ_DEDICATED_SQR
         if constexpr (N == 12) return sqr_outlined(*this);
@@ -346,35 +442,7 @@ struct Fe {
             if (i < N - 1) T[2 * i + 1] = madc_hi_cc(a.l[i], a.l[i], T[2 * i + 1]);
             else T[2 * i + 1] = madc_hi(a.l[i], a.l[i], T[2 * i + 1]);
         }
-        // word-serial Montgomery reduction on the interleaved (E, O) frame used by the product
-        uint32_t E[N], O[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) { E[j] = T[j]; O[j] = 0; }
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-            reduce_step(E, O);
-            // frame >>= 32: new E = O + (old E[1] at limb 0), new O = old E >> 64; then add T[N+i] at limb N-1
-            uint32_t nE[N], nO[N];
-            nE[0] = add_cc(O[0], E[1]);
-#pragma unroll
-            for (int j = 1; j < N - 1; j++) nE[j] = addc_cc(O[j], 0);
-            nE[N - 1] = addc_cc(O[N - 1], T[N + i]);
-            uint32_t top = addc(0, 0);
-#pragma unroll
-            for (int j = 0; j < N - 2; j++) nO[j] = E[j + 2];
-            nO[N - 2] = 0;
-            nO[N - 1] = top;   // carry out of limb N-1 has weight 2^(32N) = O[N-1]
-#pragma unroll
-            for (int j = 0; j < N; j++) { E[j] = nE[j]; O[j] = nO[j]; }
-        }
-        // value = E + O*2^32 (already shifted): fold
-        Fe r;
-        r.l[0] = E[0];
-        r.l[1] = add_cc(E[1], O[0]);
-#pragma unroll
-        for (int j = 2; j < N; j++) r.l[j] = addc_cc(E[j], O[j - 1]);
-        r.final_sub();
-        return r;
+        return mont_reduce_wide(T);
     }
 
     // E + O*2^32 += m*MOD with m chosen so that limb 0 of E becomes zero.

@@ -59,6 +59,62 @@ __global__ void __launch_bounds__(256) mb_kernel(uint32_t* out, long long* cycle
             for (int u = 0; u < MB_UNROLL; u++) { a = a * b; b = b * a; }
         }
         if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
+    } else if constexpr (MODE == 8 || MODE == 9) {
+        // DFMA issue rate (8) and DFMA + IMAD.WIDE 1:1 (9: do the two pipes run concurrently?)
+        double d[MB_CHAINS];
+        uint64_t w[MB_CHAINS];
+        const double m = __hiloint2double(0x3ff00000, y & 0xff), c = __hiloint2double(0x3e000000, z);
+#pragma unroll
+        for (int k = 0; k < MB_CHAINS; k++) { d[k] = (double)(tid + k); w[k] = ((uint64_t)tid << 32) | (tid + k); }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < MB_UNROLL; u++) {
+#pragma unroll
+                for (int k = 0; k < MB_CHAINS; k++) {
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[k]) : "d"(m), "d"(c));
+                    if constexpr (MODE == 9) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"((uint32_t)w[(k + 1) % MB_CHAINS]), "r"(y));
+                }
+            }
+        }
+        double acc = 0;
+        uint64_t wa = 0;
+#pragma unroll
+        for (int k = 0; k < MB_CHAINS; k++) { acc += d[k]; wa ^= w[k]; }
+        if (acc == 0.12345 || wa == 0x12345678u) out[tid] = 1;
+    } else if constexpr (MODE == 10) {
+        Fq a, b;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; }
+        a.l[11] &= 0x0fffffff; b.l[11] &= 0x0fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+            for (int u = 0; u < MB_UNROLL; u++) { a = Fq::mul_dfma(a, b); b = Fq::mul_dfma(b, a); }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
+    } else if constexpr (MODE == 11) {
+        Fr a, b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; }
+        a.l[7] &= 0x3fffffff; b.l[7] &= 0x3fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+            for (int u = 0; u < MB_UNROLL; u++) { a = Fr::mul_dfma(a, b); b = Fr::mul_dfma(b, a); }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
+    } else if constexpr (MODE == 12) {
+        // two independent chains per thread, one on each pipe
+        Fq a, b, c, d;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; c.l[i] = tid * 5 + i; d.l[i] = tid * 7 + i * z; }
+        a.l[11] &= 0x0fffffff; b.l[11] &= 0x0fffffff; c.l[11] &= 0x0fffffff; d.l[11] &= 0x0fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 2
+            for (int u = 0; u < MB_UNROLL / 2; u++) {
+                a = Fq::mul_inline(a, b); c = Fq::mul_dfma(c, d);
+                b = Fq::mul_inline(b, a); d = Fq::mul_dfma(d, c);
+            }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1] ^ c.l[0] ^ d.l[2];
     } else if constexpr (MODE == 5) {
         Fr a, b;
 #pragma unroll
@@ -87,7 +143,8 @@ using namespace kzg;
 extern "C" {
 
 // mode: 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE, 3 mad.lo.cc+madc.hi pair, 4 Fq mul chain, 5 Fr mul chain,
-//       6 IADD, 7 IMAD.WIDE+IADD 1:1, 100 = HBM copy (bytes = iters MiB each way)
+//       6 IADD, 7 IMAD.WIDE+IADD 1:1, 8 DFMA, 9 DFMA+IMAD.WIDE 1:1 (counts DFMA), 10/11 Fq/Fr mul_dfma chain,
+//       12 Fq: one IMAD chain + one DFMA chain per thread, 100 = HBM copy (bytes = iters MiB each way)
 // out[0] = ops/s (mode 4/5: field muls/s; mode 100: bytes moved/s), out[1] = ops per SM-clock per SM, out[2] = ms
 int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double* out) {
     KZG_REQUIRE_INIT();
@@ -130,7 +187,7 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
         KZG_CUDA(cudaEventRecord(e0, c.stream));
         switch (mode) {
 #define MB_CASE(M) case M: mb_kernel<M><<<blocks, threads, 0, c.stream>>>(d_out, d_cyc, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
-            MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7)
+            MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10) MB_CASE(11) MB_CASE(12)
 #undef MB_CASE
             default: set_error("kzgb_microbench: bad mode %d", mode); return KZGB_ERR_INVALID_ARG;
         }
@@ -144,7 +201,7 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
     cudaFree(d_out);
     cudaFree(d_cyc);
     double per_thread;
-    if (mode == 4 || mode == 5) per_thread = 2.0 * MB_UNROLL * iters;
+    if (mode == 4 || mode == 5 || mode >= 10) per_thread = 2.0 * MB_UNROLL * iters;
     else per_thread = (double)MB_CHAINS * MB_UNROLL * iters;   // mode 7 counts IMAD.WIDE only
     double total = per_thread * threads * (double)blocks;
     out[0] = total / (ms * 1e-3);

@@ -5,8 +5,9 @@
  * and the cpu_baseline / --impl reference legs of bench.py may load this
  * library.  The product (kzg_b200/) never links or calls it.
  *
- * PARITY STATUS: unpinned at the blstrs/blst boundary (see oracle/kzg_oracle.py
- * header): the reference's arithmetic lives in the un-vendored dependency
+ * PARITY STATUS: unpinned against the reference's own outputs (it cannot be run here); the
+ * group arithmetic is pinned by published blst / py_ecc known answers
+ * (tests/golden/published_kats.json).  See oracle/kzg_oracle.py's header: the reference's arithmetic lives in the un-vendored dependency
  * blstrs (proxima-one fork @ b98fc83, Cargo.toml:27) -> blst, which cannot be
  * built here (no Rust toolchain, sources absent).  This file restates the
  * published algorithms (Montgomery arithmetic over 64-bit limbs, Jacobian G1,

@@ -6,7 +6,9 @@ to the reference's root).  Only `tests/`, `__graft_entry__.smoke()` and the
 `cpu_baseline` / `--impl reference` legs of `bench.py` may import this module.
 The product path (`kzg_b200/`) never does.
 
-PARITY STATUS: **unpinned at the blstrs/blst boundary**.  The reference's field
+PARITY STATUS: the reference itself cannot be run here, so parity is **unpinned against
+the reference's own outputs**; the blst-level arithmetic IS pinned by published known
+answers of the blst family (below).  The reference's field
 and curve arithmetic (including `G1Projective::multi_exp`) lives in the
 un-vendored git dependency `blstrs` (proxima-one fork, rev b98fc83,
 Cargo.toml:27) which wraps `blst`; neither is under /root/reference and there
@@ -17,6 +19,10 @@ pins this oracle instead (see `tests/test_oracle.py`):
     and evaluation KATs, polynomial.rs:666-690 interpolation property),
   * published BLS12-381 constants (generator compression 97f1d3a7...c6bb,
     2*G = a572cbea...0f4e, root of unity of order 2^32, Montgomery constants),
+  * published known answers produced by independent implementations (blst / py_ecc,
+    Ethereum consensus-spec BLS vectors; tests/golden/published_kats.json): compressed
+    k*G for k = 1..5 and three full-width secret-key -> public-key pairs, reproduced by
+    this file, by oracle/kzg_cpu.c and by the CUDA MSM,
   * closed forms under a known SRS secret: commit(p) = p(s)*G,
     witness = ((p(s)-y)/(s-x))*G, batched w = ((p(s)-r(s))/Z(s))*G,
   * differential structure mirrored from the reference's tests (NTT vs naive

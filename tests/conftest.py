@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def published_kats():
+    """Known answers published by independent implementations (see the file's _source)."""
+    with open(os.path.join(ROOT, "tests", "golden", "published_kats.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def gpu():
     """Initialises the CUDA library on cuda:0; GPU tests fail loudly (no fallback) if that is impossible."""
     from kzg_b200 import _ffi
