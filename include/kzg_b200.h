@@ -181,6 +181,20 @@ KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t wor
                                   void* stream);
 KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint32_t batch, int inverse,
                                 const kzgb_fr* scale, void* stream);
+/* Fused column pass + exchange over NVLink peer memory (replaces columns + all-to-all + unpack): element (k1, c)
+ * of the column pass is stored directly into the row matrix of the rank that owns row k1, already transposed:
+ * peer_rows[k1 / (N1/world)][(k1 mod (N1/world)) * N2 + rank*C + c].  peer_rows: host array of `world` device
+ * pointers valid on this device (peer_rows[rank] local, the others CUDA-IPC mappings: kzgb_peer_*).  The slab is
+ * only read.  The caller puts a barrier between this call and kzgb_ntt_batch_dev on the rows. */
+KZGB_API int kzgb_ntt4_columns_scatter_dev(const void* d_slab, void* const* peer_rows, uint32_t world, uint32_t rank,
+                                           uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
+                                           int inverse, void* stream);
+/* peer memory: cudaMalloc + a 64-byte CUDA IPC handle to send to the other ranks of the node; open / close a
+ * peer's handle (enables peer access lazily); free what kzgb_peer_alloc returned */
+KZGB_API int kzgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]);
+KZGB_API int kzgb_peer_open(const unsigned char handle[64], void** d_ptr);
+KZGB_API int kzgb_peer_close(void* d_ptr);
+KZGB_API int kzgb_peer_free(void* d_ptr);
 
 /* ---- EvaluationDomain helpers off the prover path: element-wise passes and the coset transforms.
  * op 0: a[i] *= b[i]  (mul_assign, ft.rs:220-244)      op 1: a[i] -= b[i]  (sub_assign, ft.rs:247-271)

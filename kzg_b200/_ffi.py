@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkzg_b200.so")
+LIB_PATH = os.environ.get("KZGB_LIB") or os.path.join(_HERE, "libkzg_b200.so")   # KZGB_LIB: A/B builds of the library
 
 KZGB_OK = 0
 KZGB_POINT_NOT_ON_POLYNOMIAL = 1
@@ -333,6 +333,39 @@ def ntt4_columns_dev(d_slab: int, log_n: int, log_n1: int, log_c: int, col_offse
 def ntt4_unpack_dev(d_recv: int, d_rows: int, world: int, nrows: int, cols: int, stream: int = 0):
     return check(lib().kzgb_ntt4_unpack_dev(C.c_void_p(d_recv), C.c_void_p(d_rows), C.c_uint32(world), C.c_uint32(nrows),
                                             C.c_uint32(cols), C.c_void_p(stream)))
+
+
+def ntt4_columns_scatter_dev(d_slab: int, peer_rows, rank: int, log_n: int, log_n1: int, log_c: int, col_offset: int,
+                             inverse: bool, stream: int = 0):
+    """Fused column pass + exchange: results go straight into the peers' row matrices (device pointers, one per rank)."""
+    world = len(peer_rows)
+    arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_rows])
+    return check(lib().kzgb_ntt4_columns_scatter_dev(C.c_void_p(d_slab), arr, C.c_uint32(world), C.c_uint32(rank),
+                                                     C.c_uint32(log_n), C.c_uint32(log_n1), C.c_uint32(log_c),
+                                                     C.c_uint32(col_offset), C.c_int(int(inverse)), C.c_void_p(stream)))
+
+
+def peer_alloc(nbytes: int):
+    """(device pointer, 64-byte CUDA IPC handle) of a fresh cudaMalloc allocation other ranks can map."""
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64)()
+    check(lib().kzgb_peer_alloc(C.c_size_t(nbytes), C.byref(p), h))
+    return int(p.value), bytes(h)
+
+
+def peer_open(handle: bytes) -> int:
+    p = C.c_void_p()
+    h = (C.c_ubyte * 64).from_buffer_copy(handle)
+    check(lib().kzgb_peer_open(h, C.byref(p)))
+    return int(p.value)
+
+
+def peer_close(d_ptr: int) -> None:
+    check(lib().kzgb_peer_close(C.c_void_p(d_ptr)))
+
+
+def peer_free(d_ptr: int) -> None:
+    check(lib().kzgb_peer_free(C.c_void_p(d_ptr)))
 
 
 def ntt_batch_dev(d_inout: int, d_tmp: int, log_n: int, batch: int, inverse: bool, scale=None, stream: int = 0):

@@ -42,6 +42,7 @@ KZG_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm vo
 // --------------------------------------------------------------------------
 struct FqParams {
     static constexpr int N = 12;
+    static constexpr bool LOW_LIMBS_1_FFFFFFFF = false;
     // p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
     __host__ __device__ static constexpr uint32_t mod(int i) {
         constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -71,6 +72,11 @@ static __constant__ uint32_t FR_INV32_C[1] = {0xffffffffu};
 
 struct FrParams {
     static constexpr int N = 8;
+#ifdef KZG_FR_SPECIAL_REDUCE   // experiment, measured slower (profiles/experiments/README.md): off by default
+    static constexpr bool LOW_LIMBS_1_FFFFFFFF = true;   // r = ...ffffffff00000001: see reduce_step
+#else
+    static constexpr bool LOW_LIMBS_1_FFFFFFFF = false;
+#endif
     // r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
     __host__ __device__ static constexpr uint32_t mod(int i) {
         constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
@@ -447,6 +453,38 @@ struct Fe {
 
     // E + O*2^32 += m*MOD with m chosen so that limb 0 of E becomes zero.
     KZG_DI static void reduce_step(uint32_t* E, uint32_t* O) {
+        if constexpr (P::LOW_LIMBS_1_FFFFFFFF) {
+            // MOD = 1 + 0xffffffff*2^32 + ... (Fr): m = -E0 and m*(1 + (2^32-1)*2^32) + E0 =
+            // (E0+1)*2^32 + (~E0)*2^64 for E0 != 0 (and 0 for E0 == 0), so the two lowest partial products of
+            // every round are three integer additions on the ALU pipe instead of two wide multiply-adds on the
+            // FMA-heavy pipe: 6 instead of 8 wide mads per round, 120 instead of 136 per Fr product.  Bit-exact
+            // (94 GPU tests pass with it), Fr multiply chain +3 %, but the NTT gets 5 % SLOWER (0.984 vs 0.936 ms at
+            // 2^22): the compare/select/carry instructions lengthen the dependent chain.  Kept as an opt-in
+            // experiment (-DKZG_FR_SPECIAL_REDUCE).  Limb-level model: scripts/fr_reduce_model.py.
+            const uint32_t e0 = E[0];
+            const uint32_t m = e0 * P::inv32();
+            const uint32_t nz = e0 != 0 ? 1u : 0u;
+            const uint32_t c = e0 == 0xffffffffu ? 1u : 0u;
+            const uint32_t add1 = e0 + nz;        // limb 1 (wraps to 0 with c = 1 when e0 = 2^32-1)
+            const uint32_t add2 = m - nz + c;     // limb 2
+            O[1] = add_cc(O[1], add2);
+#pragma unroll
+            for (int j = 2; j < N - 2; j += 2) {
+                O[j] = madc_lo_cc(P::mod(j + 1), m, O[j]);
+                O[j + 1] = madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
+            }
+            O[N - 2] = madc_lo_cc(P::mod(N - 1), m, O[N - 2]);
+            O[N - 1] = madc_hi(P::mod(N - 1), m, O[N - 1]);
+            E[0] = 0;
+            E[1] = add_cc(E[1], add1);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                E[j] = madc_lo_cc(P::mod(j), m, E[j]);
+                E[j + 1] = madc_hi_cc(P::mod(j), m, E[j + 1]);
+            }
+            O[N - 1] = addc(O[N - 1], 0);
+            return;
+        }
         const uint32_t m = E[0] * P::inv32();
         O[0] = mad_lo_cc(P::mod(1), m, O[0]);
         O[1] = madc_hi_cc(P::mod(1), m, O[1]);

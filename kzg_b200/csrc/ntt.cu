@@ -17,6 +17,7 @@
 // (omega^-e = -omega^(N/2-e)), and every stage of every pass.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "field.cuh"
@@ -91,9 +92,20 @@ KZG_DI Fr twiddle(const Fr* __restrict__ tw, uint32_t e, uint32_t log_n, uint32_
     return ldg_fr(&tw[e & (half - 1)]);
 }
 
-template <bool LAST>
+// Fused four-step exchange (multi-GPU): instead of storing the column pass's result back into the local slab and
+// handing it to an all-to-all, the epilogue stores element (k1, col) straight into the row matrix of the rank
+// that owns row k1 -- peer memory mapped over NVLink (CUDA IPC) -- at rows[k1 mod rpr][rank*C + col], i.e. already
+// transposed into the layout the row pass wants.  Each (k1, tile) is a contiguous T*32-byte peer store.
+constexpr int NTT_MAX_PEERS = 16;
+struct NttScatter {
+    Fr* peer[NTT_MAX_PEERS];   // rows buffer of every rank (peer[rank] is local)
+    uint32_t log_rpr;          // log2(rows per rank) = log_n1 - log2(world)
+    uint32_t rank, log_world, log_c;
+};
+
+template <bool LAST, bool SCATTER>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
-                                                               NttPassParams p, Fr minv) {
+                                                               NttPassParams p, Fr minv, NttScatter sc) {
     extern __shared__ uint4 sm[];
     const uint32_t tid = threadIdx.x;
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t;
@@ -200,7 +212,13 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
                 v = v * w;
                 if (neg) v = v.neg();
             }
-            Fr* dst = &out[base + ((uint64_t)kj << p.log_s) + tl];
+            Fr* dst;
+            if (SCATTER) {
+                const uint32_t h = kj >> sc.log_rpr, r = kj & ((1u << sc.log_rpr) - 1);
+                dst = sc.peer[h] + ((((uint64_t)r << sc.log_world) + sc.rank) << sc.log_c) + low0 + tl;
+            } else {
+                dst = &out[base + ((uint64_t)kj << p.log_s) + tl];
+            }
             sts_fr(dst, v);  // 2 x 16-byte global stores
         }
     } else {
@@ -293,8 +311,9 @@ static NttPlan ntt_plan(uint32_t log_n) {
 static bool g_ntt_attr_set = false;
 static int ntt_set_attrs() {
     if (!g_ntt_attr_set) {
-        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         g_ntt_attr_set = true;
     }
     return KZGB_OK;
@@ -303,8 +322,9 @@ static int ntt_set_attrs() {
 // Four-step, step 1 (multi-GPU NTT): this rank's slab is [N1 rows][C columns] (row-major) holding
 // a[i1*N2 + col_offset + c].  In place: N1-point transforms down every column, then the twiddle
 // omega_N^(k1 * (col_offset + c)).  One shared-memory pass (N1 <= 2^11).
+// With `scatter` != nullptr the slab is left untouched and the result goes to the peers' row matrices instead.
 int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset, bool inverse,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const NttScatter* scatter) {
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (log_n1 > NTT_MAX_TILE_LOG || log_n1 > log_n) {
         set_error("ntt_columns: log_n1 = %u out of range", log_n1);
@@ -335,7 +355,12 @@ int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c,
     Fr one;
     for (int i = 0; i < 8; i++) one.l[i] = FrParams::one(i);
     // stage twiddles: omega_N1^(j*N1/2m) = omega_N^(j*N/2m), i.e. the same ladder the kernel uses for any pass
-    ntt_pass_kernel<false><<<dim3((unsigned)tiles, 1), NTT_THREADS, smem, stream>>>(d_slab, d_slab, tw, p, one);
+    if (scatter)
+        ntt_pass_kernel<false, true><<<dim3((unsigned)tiles, 1), NTT_THREADS, smem, stream>>>(d_slab, d_slab, tw, p, one,
+                                                                                              *scatter);
+    else
+        ntt_pass_kernel<false, false><<<dim3((unsigned)tiles, 1), NTT_THREADS, smem, stream>>>(d_slab, d_slab, tw, p, one,
+                                                                                               NttScatter{});
     KZG_LAUNCHED();
     return KZGB_OK;
 }
@@ -395,8 +420,8 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         else if (last) { src = d_tmp; dst = d_data; }
         else { src = d_tmp; dst = d_tmp; }
         dim3 grid((unsigned)tiles, batch);
-        if (last) ntt_pass_kernel<true><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
-        else ntt_pass_kernel<false><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv);
+        if (last) ntt_pass_kernel<true, false><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv, NttScatter{});
+        else ntt_pass_kernel<false, false><<<grid, NTT_THREADS, smem, stream>>>(src, dst, tw, p, minv, NttScatter{});
         KZG_LAUNCHED();
     }
     return KZGB_OK;
@@ -446,6 +471,75 @@ KZGB_API int kzgb_ntt4_columns_dev(void* d_slab, uint32_t log_n, uint32_t log_n1
     if (!d_slab) { set_error("kzgb_ntt4_columns_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
     return ntt_columns_run((Fr*)d_slab, log_n, log_n1, log_c, col_offset, inverse != 0, st);
+}
+
+// Fused column pass + exchange: like kzgb_ntt4_columns_dev, but element (k1, c) of the result is stored straight
+// into peer_rows[k1 / (N1/world)] (device pointers valid on THIS device: local memory or CUDA-IPC mappings of the
+// peers' row matrices, host array of `world` entries) at rows[k1 mod (N1/world)][rank*C + c].  The slab is only
+// read.  The caller orders the ranks (a barrier) between this call and the row pass.
+KZGB_API int kzgb_ntt4_columns_scatter_dev(const void* d_slab, void* const* peer_rows, uint32_t world, uint32_t rank,
+                                           uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
+                                           int inverse, void* stream) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    if (!d_slab || !peer_rows) { set_error("kzgb_ntt4_columns_scatter_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
+    uint32_t lw = 0;
+    while ((1u << lw) < world) lw++;
+    if (world == 0 || (1u << lw) != world || world > (uint32_t)NTT_MAX_PEERS || rank >= world || lw > log_n1) {
+        set_error("kzgb_ntt4_columns_scatter_dev: world = %u (power of two <= %d, <= N1), rank = %u", world, NTT_MAX_PEERS,
+                  rank);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    NttScatter sc{};
+    for (uint32_t i = 0; i < world; i++) {
+        if (!peer_rows[i]) { set_error("kzgb_ntt4_columns_scatter_dev: peer %u is null", i); return KZGB_ERR_INVALID_ARG; }
+        sc.peer[i] = (Fr*)peer_rows[i];
+    }
+    sc.log_rpr = log_n1 - lw;
+    sc.rank = rank;
+    sc.log_world = lw;
+    sc.log_c = log_c;
+    cudaStream_t st = use_stream((cudaStream_t)stream);
+    return ntt_columns_run((Fr*)d_slab, log_n, log_n1, log_c, col_offset, inverse != 0, st, &sc);
+}
+
+// ---- peer memory for the fused exchange: plain cudaMalloc + CUDA IPC handles (one process per GPU) ----
+KZGB_API int kzgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    if (!d_ptr || !handle || bytes == 0) { set_error("kzgb_peer_alloc: bad argument"); return KZGB_ERR_INVALID_ARG; }
+    void* p = nullptr;
+    KZG_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__); }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return KZGB_OK;
+}
+KZGB_API int kzgb_peer_open(const unsigned char handle[64], void** d_ptr) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    if (!d_ptr || !handle) { set_error("kzgb_peer_open: bad argument"); return KZGB_ERR_INVALID_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    KZG_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KZGB_OK;
+}
+KZGB_API int kzgb_peer_close(void* d_ptr) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_CUDA(cudaDeviceSynchronize());
+    KZG_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return KZGB_OK;
+}
+KZGB_API int kzgb_peer_free(void* d_ptr) {
+    KZG_REQUIRE_INIT();
+    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_CUDA(cudaDeviceSynchronize());
+    KZG_CUDA(cudaFree(d_ptr));
+    return KZGB_OK;
 }
 
 KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t world, uint32_t nrows, uint32_t cols,

@@ -146,3 +146,128 @@ def ntt_four_step(slab: torch.Tensor, log_n: int, inverse: bool = False, ops=Non
     scale = fr(pow(1 << log_n, -1, R_MOD)) if inverse else None
     ops.rows(rows, l2, inverse, scale)
     return rows
+
+
+# ---------------------------------------------------------------------------
+# Fused exchange: the column pass stores straight into the peers' row matrices over NVLink
+# ---------------------------------------------------------------------------
+class _DeviceBuffer:
+    """Wraps a raw device allocation so torch can view it (no copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+class CudaPeerOps:
+    """Peer memory (cudaMalloc + CUDA IPC) and the two kernels of the fused four-step NTT, behind the C ABI."""
+
+    def peer_alloc(self, nbytes: int):
+        return _ffi.peer_alloc(nbytes)
+
+    def peer_open(self, handle: bytes) -> int:
+        return _ffi.peer_open(handle)
+
+    def peer_close(self, ptr: int) -> None:
+        _ffi.peer_close(ptr)
+
+    def peer_free(self, ptr: int) -> None:
+        _ffi.peer_free(ptr)
+
+    def wrap(self, ptr: int, nbytes: int) -> torch.Tensor:
+        return torch.as_tensor(_DeviceBuffer(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def token(self) -> torch.Tensor:
+        return torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def drain(self) -> None:
+        torch.cuda.synchronize()
+
+    def columns_scatter(self, slab, peers, rank, log_n, log_n1, log_c, col_offset, inverse):
+        _ffi.ntt4_columns_scatter_dev(slab.data_ptr(), peers, rank, log_n, log_n1, log_c, col_offset, inverse,
+                                      torch.cuda.current_stream().cuda_stream)
+
+    def rows(self, rows: torch.Tensor, log_n2, inverse, scale):
+        CudaNttOps().rows(rows, log_n2, inverse, scale)
+
+
+class FourStepPeerPlan:
+    """Peer-memory plan of the fused four-step NTT for one (log_n, world): every rank owns TWO row matrices
+    [N1/G, N2] allocated with cudaMalloc and mapped into every other rank through CUDA IPC (one process per GPU,
+    one node; NVLink/NVSwitch carries the stores).  Calls alternate between the two matrices, so a single barrier
+    per call (after the column pass) is enough: a rank can only be writing matrix k%2 of call k after every rank has
+    passed the barrier of call k-1, i.e. after every rank finished the row pass of call k-2 that last read it."""
+
+    def __init__(self, log_n: int, group=None, log_n1: Optional[int] = None, ops=None):
+        self.ops = ops or CudaPeerOps()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.log_n = log_n
+        self.l1, self.l2, self.lc = four_step_shape(log_n, self.world, log_n1)
+        self.nrows = (1 << self.l1) // self.world
+        self.nbytes = self.nrows * (1 << self.l2) * 32
+        self.calls = 0
+        self.local = []          # my two matrices (pointers)
+        handles = []
+        for _ in range(2):
+            p, h = self.ops.peer_alloc(self.nbytes)
+            self.local.append(p)
+            handles.append(h)
+        gathered = [handles]
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handles, group=group)
+        self._opened = []
+        self.peers = [[], []]    # peers[k][g] = matrix k of rank g as seen from this rank
+        for k in range(2):
+            for g in range(self.world):
+                if g == self.rank:
+                    self.peers[k].append(self.local[k])
+                else:
+                    q = self.ops.peer_open(gathered[g][k])
+                    self._opened.append(q)
+                    self.peers[k].append(q)
+        self._token = None
+
+    def rows_tensor(self, k: int) -> torch.Tensor:
+        return self.ops.wrap(self.local[k], self.nbytes).view(self.nrows, 1 << self.l2, 4)
+
+    def barrier(self):
+        """Stream-ordered barrier (a 1-element all-reduce): no host synchronisation on the CUDA path."""
+        if self.world > 1:
+            if self._token is None:
+                self._token = self.ops.token()
+            dist.all_reduce(self._token, group=self.group)
+
+    def close(self):
+        if not self.local:
+            return
+        self.ops.drain()
+        if self.world > 1:
+            dist.barrier(group=self.group)     # nobody is still storing into a matrix that is about to go away
+        for q in self._opened:
+            self.ops.peer_close(q)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self.local:
+            self.ops.peer_free(p)
+        self.local, self._opened = [], []
+
+
+def ntt_four_step_fused(slab: torch.Tensor, plan: FourStepPeerPlan, inverse: bool = False) -> torch.Tensor:
+    """Distributed NTT with the exchange fused into the column pass: same input slab and same result block as
+    `ntt_four_step`, but the column kernel's epilogue stores each element directly into the row matrix of the rank
+    that owns its row (peer memory over NVLink), already transposed -- no all-to-all, no unpack pass; one
+    stream-ordered barrier separates the two passes.  The slab is only read.  Returns a view of the plan's row
+    matrix (valid until the plan's next-but-one call)."""
+    n1, c = 1 << plan.l1, 1 << plan.lc
+    assert tuple(slab.shape) == (n1, c, 4), f"slab shape {tuple(slab.shape)} != {(n1, c, 4)}"
+    k = plan.calls & 1
+    plan.calls += 1
+    plan.ops.columns_scatter(slab, plan.peers[k], plan.rank, plan.log_n, plan.l1, plan.lc, plan.rank * c, inverse)
+    plan.barrier()
+    rows = plan.rows_tensor(k)
+    from .scalar import R_MOD, fr
+    scale = fr(pow(1 << plan.log_n, -1, R_MOD)) if inverse else None
+    plan.ops.rows(rows, plan.l2, inverse, scale)
+    return rows

@@ -65,4 +65,44 @@ t = torch.tensor([tot / K], device=dev, dtype=torch.float64)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print("four-step NTT 2^%d on %d GPU(s): %.3f ms (max over ranks)" % (LOG, world, t.item()), flush=True)
+# ---- fused exchange: column pass stores into the peers' row matrices (CUDA IPC over NVLink) ----
+plan = kd.FourStepPeerPlan(LOG)
+ok = True
+for it in range(4):           # alternates the two row matrices; inverse on odd calls
+    inv = bool(it & 1)
+    work.copy_(slab)
+    ref = kd.ntt_four_step(work, LOG, inv)
+    fused = kd.ntt_four_step_fused(slab, plan, inv)
+    ok = ok and bool(torch.equal(ref, fused))
+torch.cuda.synchronize()
+okt = torch.tensor([1 if ok else 0], device=dev)
+if world > 1: dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("fused four-step NTT 2^%d == all-to-all version on every rank (4 calls, fwd/inv):" % LOG, bool(okt.item()), flush=True)
+for _ in range(3): kd.ntt_four_step_fused(slab, plan, False)
+torch.cuda.synchronize()
+if world > 1: dist.barrier()
+K = 10
+tot = 0.0
+for _ in range(K):
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    e0.record(); kd.ntt_four_step_fused(slab, plan, False); e1.record()
+    torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+t = torch.tensor([tot / K], device=dev, dtype=torch.float64)
+if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# back-to-back (no host sync between calls): K calls in one timed region
+torch.cuda.synchronize()
+if world > 1: dist.barrier()
+e0.record()
+for _ in range(K): kd.ntt_four_step_fused(slab, plan, False)
+e1.record()
+torch.cuda.synchronize()
+t2 = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
+if world > 1: dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("fused four-step NTT 2^%d on %d GPU(s): %.3f ms per isolated call, %.3f ms back to back (max over ranks)"
+          % (LOG, world, t.item(), t2.item()), flush=True)
+plan.close()
 if world > 1: dist.destroy_process_group()

@@ -79,6 +79,62 @@ class OracleNttOps:
         rows.copy_(_from_np(a))
 
 
+class OraclePeerOps(OracleNttOps):
+    """Stand-in for CudaPeerOps on CPU: "peer memory" is a named POSIX shared-memory segment (the name plays the
+    role of the CUDA IPC handle), pointers are indices into a local registry."""
+
+    def __init__(self, cpu):
+        super().__init__(cpu)
+        self.segs = {}
+
+    def peer_alloc(self, nbytes):
+        from multiprocessing import shared_memory
+        seg = shared_memory.SharedMemory(create=True, size=nbytes)
+        ptr = len(self.segs) + 1
+        self.segs[ptr] = seg
+        return ptr, seg.name.encode()
+
+    def peer_open(self, handle):
+        from multiprocessing import shared_memory
+        seg = shared_memory.SharedMemory(name=handle.decode())
+        ptr = len(self.segs) + 1
+        self.segs[ptr] = seg
+        return ptr
+
+    def peer_close(self, ptr):
+        self.segs.pop(ptr).close()
+
+    def peer_free(self, ptr):
+        seg = self.segs.pop(ptr)
+        seg.close()
+        seg.unlink()
+
+    def _view(self, ptr, nbytes=None):
+        seg = self.segs[ptr]
+        return np.ndarray(((nbytes or seg.size) // 8,), dtype=np.uint64, buffer=seg.buf)
+
+    def wrap(self, ptr, nbytes):
+        return torch.from_numpy(self._view(ptr, nbytes).view(np.int64))
+
+    def token(self):
+        return torch.zeros(1, dtype=torch.int32)
+
+    def drain(self):
+        pass
+
+    def columns_scatter(self, slab, peers, rank, log_n, log_n1, log_c, col_offset, inverse):
+        tmp = slab.clone()
+        self.columns(tmp, log_n, log_n1, log_c, col_offset, inverse)      # the unfused column pass ...
+        a = _to_np(tmp).reshape(1 << log_n1, 1 << log_c, 4)
+        world, C = len(peers), 1 << log_c
+        rpr = (1 << log_n1) // world
+        n2 = world * C
+        for k1 in range(1 << log_n1):                                    # ... stored where the fused kernel stores it
+            h, r = divmod(k1, rpr)
+            dst = self._view(peers[h]).reshape(rpr, n2, 4)
+            dst[r, rank * C:(rank + 1) * C] = a[k1]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -113,6 +169,18 @@ def _worker(rank, world, port, q):
             dist.all_gather(gathered, rows)
             full = kd.four_step_gather([_to_np(g) for g in gathered], log_n, world, log_n1=3)
             oks.append(bool((full == cpu.fft(vec, log_n, inverse, 1)).all()))
+        # ---- fused four-step (peer-memory stores instead of all-to-all + unpack): same blocks, slab untouched ----
+        plan = kd.FourStepPeerPlan(log_n, log_n1=3, ops=OraclePeerOps(cpu))
+        for inverse in (False, True, False):   # three calls: both row matrices and the reuse of the first
+            slabs = kd.four_step_scatter(vec, log_n, world, log_n1=3)
+            mine = _from_np(slabs[rank]).clone()
+            rows = kd.ntt_four_step_fused(mine, plan, inverse).clone()
+            assert (_to_np(mine) == slabs[rank]).all()
+            gathered = [torch.empty_like(rows) for _ in range(world)]
+            dist.all_gather(gathered, rows)
+            full = kd.four_step_gather([_to_np(g) for g in gathered], log_n, world, log_n1=3)
+            oks.append(bool((full == cpu.fft(vec, log_n, inverse, 1)).all()))
+        plan.close()
         q.put((rank, ok_msm, oks))
     finally:
         dist.destroy_process_group()
@@ -155,4 +223,4 @@ def test_world_size_2_gloo_msm_and_ntt():
         assert p.exitcode == 0
     for rank, ok_msm, oks in results:
         assert ok_msm, f"rank {rank}: sharded MSM mismatch"
-        assert oks == [True, True], f"rank {rank}: four-step NTT mismatch {oks}"
+        assert oks == [True] * 5, f"rank {rank}: four-step NTT mismatch {oks} (unfused fwd/inv, fused fwd/inv/fwd)"

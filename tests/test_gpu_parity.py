@@ -362,6 +362,43 @@ def test_four_step_blocks_emulated_ranks(gpu, cpu, log_n, world, inverse):
         assert (full == cpu.fft(vec, log_n, inverse, 8)).all()
 
 
+@pytest.mark.parametrize("log_n,world,inverse", [(8, 2, False), (12, 4, True), (16, 8, False), (20, 2, True), (20, 16, False)])
+def test_four_step_fused_scatter_emulated_ranks(gpu, cpu, log_n, world, inverse):
+    """The fused column pass (epilogue stores straight into the owners' row matrices, here all on this GPU: the
+    peer pointers are local) + the row pass == the single-GPU transform; the slab is left untouched.  The row
+    matrices go through kzgb_peer_alloc and an IPC handle is produced for each (opened only across processes)."""
+    import torch
+    from kzg_b200 import distributed as kd
+    vec = cpu.fr_stream(5, 1 << log_n)
+    l1, l2, lc = kd.four_step_shape(log_n, world)
+    n1, c = 1 << l1, 1 << lc
+    nrows = n1 // world
+    pops = kd.CudaPeerOps()
+    nbytes = nrows * (1 << l2) * 32
+    allocs = [pops.peer_alloc(nbytes) for _ in range(world)]
+    assert all(len(h) == 64 for _, h in allocs)
+    peers = [p for p, _ in allocs]
+    host_slabs = kd.four_step_scatter(vec, log_n, world)
+    slabs = [torch.from_numpy(s.view(np.int64)).cuda() for s in host_slabs]
+    for g in range(world):
+        pops.columns_scatter(slabs[g], peers, g, log_n, l1, lc, g * c, inverse)
+    torch.cuda.synchronize()
+    blocks = []
+    scale = scalar.fr(pow(1 << log_n, -1, R)) if inverse else None
+    for h in range(world):
+        rows = pops.wrap(peers[h], nbytes).view(nrows, 1 << l2, 4)
+        pops.rows(rows, l2, inverse, scale)
+        torch.cuda.synchronize()
+        blocks.append(rows.cpu().numpy().view(np.uint64))
+    for g in range(world):
+        assert (slabs[g].cpu().numpy().view(np.uint64) == host_slabs[g]).all()
+    full = kd.four_step_gather(blocks, log_n, world)
+    assert (full == gpu.ntt(vec, log_n, inverse)[1]).all()
+    del rows
+    for p in peers:
+        pops.peer_free(p)
+
+
 def test_batched_witness_more_points_than_coefficients(gpu, cpu):
     """coeff_form.rs:377-398 generalised: m >= n openings of a degree-(n-1) polynomial -> psi = 0, identity witness;
     a wrong value is still rejected (numerator of degree < m must be the zero polynomial)."""
