@@ -3,10 +3,15 @@
 
 metric : BLS12-381 G1 MSM points/sec (commit, n=2^20)   [BASELINE.json]; Fr NTT 2^22 ms is reported in `extra`.
 step   : one KZGProver::commit of a degree-(2^20 - 1) polynomial = one G1 MSM over 2^20 SRS points per GPU.
-value  : points/s with scalars and SRS resident in HBM (CUDA events on the launching stream, max over ranks).
-e2e    : the same through the C ABI's host-pointer call kzgb_msm_g1 (pinned host scalars in, affine point out).
-N > 1  : weak scaling -- every rank holds its own 2^20-point shard of an N*2^20-point SRS, partial sums are
-         all-gathered (192 B per rank) over NCCL and combined on every rank.
+value  : points/s with scalars and SRS resident in HBM (CUDA events on the launching stream, max over ranks).  The K
+         timed steps are K independent commits issued through the pipelined batch entry point
+         (kzgb_msm_g1_batch_dev: the latency-bound tail of commit i overlaps the sort/accumulation of commit i+1);
+         the same K commits issued one call at a time are timed as well (extra.sequential) and it is THAT pass whose
+         per-kernel CUDA-event durations feed `roofline` and `stage_ms` (overlapped kernels have no clean duration).
+e2e    : the same K commits through the C ABI's host-pointer call kzgb_msm_g1_batch (pinned host scalars in, affine
+         points out; every commit's 32 MiB H2D and 96 B D2H are inside the timed region).
+N > 1  : weak scaling -- every rank holds its own 2^20-point shard of an N*2^20-point SRS, the K partial sums per rank
+         are all-gathered (K x 192 B per rank) over NCCL and combined on every rank.
 --impl reference : the reference's CPU path (C restatement in oracle/, all host threads) on a bounded sample.
 """
 import argparse
@@ -163,6 +168,9 @@ def run_gpu(args):
     def step(i):
         return kd.sharded_msm(srs, polys[i % NBUF], ops)
 
+    def steps_pipelined(first, count):
+        return kd.sharded_msm_many(srs, [polys[(first + i) % NBUF] for i in range(count)], ops)
+
     # ---- parity gate: result of step 0 == p(s)*G (closed form, oracle), compared as compressed G1 ----
     out0 = step(0)
     torch.cuda.synchronize()
@@ -177,31 +185,47 @@ def run_gpu(args):
     # ---- on-box peak for the roofline denominator: dense IMAD.WIDE chains ----
     imad_peak = max(_ffi.microbench(3, 8, 256, 64)["ops_per_s"] for _ in range(3))
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(args.warmup):
         step(i)
+    steps_pipelined(0, max(args.warmup, 3))
     barrier()
-    launches0 = _ffi.launch_count()
-    _ffi.profile_enable(True)
-    _ffi.profile_read()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
+    # ---- kernel-level pass: the K commits one call at a time, stage timers on (roofline / stage_ms) ----
+    _ffi.profile_enable(True)
+    _ffi.profile_read()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms_step_seq = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    prof = _ffi.profile_read()
+    _ffi.profile_enable(False)
+    # ---- headline pass: the same K commits through the pipelined batch ----
+    launches0 = _ffi.launch_count()
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
-        for i in range(args.steps):
-            step(args.warmup + i)
+        outs = steps_pipelined(args.warmup, args.steps)
         e1.record()
         barrier()
-    ms_total = e0.elapsed_time(e1)
-    prof = _ffi.profile_read()
-    _ffi.profile_enable(False)
     launches = _ffi.launch_count() - launches0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = total_points / (ms_step * 1e-3)
+    if rank == 0 and world == 1:   # the pipelined results are the sequential ones: step `warmup` again, one call
+        chk = step(args.warmup)
+        torch.cuda.synchronize()
+        if not torch.equal(chk.view(-1), outs[0].view(-1)):
+            print(json.dumps({"error": "pipelined batch result differs from the single call"}), flush=True)
+            sys.exit(1)
 
     # ---- e2e: host-pointer C-ABI call, pinned host scalars, copies inside the timed region ----
     host_polys = [polys[b].cpu().pin_memory() for b in range(2)]
@@ -209,26 +233,54 @@ def run_gpu(args):
     import ctypes as C
     lib = _ffi.lib()
 
-    def e2e_step(i):
-        hp = host_polys[i % 2]
-        if world == 1:
-            _ffi.check(lib.kzgb_msm_g1(srs._h, C.c_void_p(hp.data_ptr()), C.c_size_t(N_POINTS), _ffi.ptr(out_host)))
-        else:
-            d = hp.to(dev, non_blocking=True)
-            o = kd.sharded_msm(srs, d, ops)
-            o.cpu()
-    for i in range(2):
-        e2e_step(i)
+    host_views = [hp.numpy().view(np.uint64) for hp in host_polys]
+
+    def e2e_steps(count):
+        if world == 1:   # the public host-pointer call: K commits, each with its own H2D and D2H
+            return srs.msm_batch([host_views[i % 2] for i in range(count)])
+        ds = [host_polys[i % 2].to(dev, non_blocking=True) for i in range(count)]
+        return kd.sharded_msm_many(srs, ds, ops).cpu()
+    e2e_steps(2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_out = e2e_steps(args.steps)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    # one call at a time through kzgb_msm_g1 (what a drop-in `commit` does), for comparison
+    e2e_seq_s = None
+    if world == 1:
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            _ffi.check(lib.kzgb_msm_g1(srs._h, C.c_void_p(host_polys[i % 2].data_ptr()), C.c_size_t(N_POINTS), _ffi.ptr(out_host)))
+        e2e_seq_s = (time.perf_counter() - t0) / args.steps
+        if not (np.asarray(e2e_out)[(args.steps - 1)] == out_host).all():
+            print(json.dumps({"error": "host batch result differs from the single call"}), flush=True)
+            sys.exit(1)
+
+    # ---- N > 1: four-step Fr NTT 2^24 across the ranks (config C5), fused peer-memory exchange vs NCCL all-to-all ----
+    ntt4 = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+        LOG4 = 24
+        plan = kd.FourStepPeerPlan(LOG4)
+        slab = torch.empty((1 << plan.l1, 1 << plan.lc, 4), dtype=torch.int64, device=dev)
+        _ffi.fr_stream_dev(slab.data_ptr(), 5, slab.shape[0] * slab.shape[1], start=rank * slab.shape[0] * slab.shape[1], stream=stream)
+        work4 = slab.clone()
+        res = {}
+        for name, fn in (("fused_peer_store_ms", lambda: kd.ntt_four_step_fused(slab, plan, False)),
+                         ("nccl_all_to_all_ms", lambda: kd.ntt_four_step(work4, LOG4, False))):
+            for _ in range(3):
+                fn()
+            barrier()
+            e0.record()
+            for _ in range(10):
+                fn()
+            e1.record()
+            barrier()
+            res[name] = max_over_ranks(e0.elapsed_time(e1)) / 10
+        plan.close()
+        ntt4 = {"log_n": LOG4, **res, "note": "strong scaling: one 2^24 transform split over the ranks; bit-exact parity of both "
+                "variants with the single-GPU transform: scripts/dist_check.py, profiles/r01g_dist_check_fused_n*.log"}
+        del slab, work4
 
     if rank != 0:
         if world > 1:
@@ -237,7 +289,13 @@ def run_gpu(args):
     stage_ms = {k: v[0] / v[1] for k, v in prof.items()}
     acc_ms = stage_ms.get("msm_accumulate")
     extra = {"stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "window_bits": srs.window_bits,
-             "srs_table_bytes": srs.device_bytes}
+             "srs_table_bytes": srs.device_bytes,
+             "sequential": {"ms_per_step": ms_step_seq, "value": total_points / (ms_step_seq * 1e-3),
+                            "e2e_ms_per_step": e2e_seq_s * 1e3 if e2e_seq_s else None,
+                            "e2e_value": N_POINTS / e2e_seq_s if e2e_seq_s else None,
+                            "note": "the same K commits issued one call at a time (kzgb_msm_g1_dev / kzgb_msm_g1); stage_ms and roofline come from this pass"}}
+    if ntt4:
+        extra["ntt_2p24_four_step"] = ntt4
     roofline = None
     if acc_ms:
         achieved = IMAD_PER_POINT_ACC * N_POINTS / (acc_ms * 1e-3)
@@ -250,7 +308,8 @@ def run_gpu(args):
                     "unit": "TIMAD/s (32x32->64 multiply-adds)", "frac": achieved / imad_peak, "traffic": traffic,
                     "peak_source": "measured live: kzgb_microbench mode 3 (dense independent IMAD.WIDE.U32 chains)",
                     "algorithmic_work": "16 windows x 3000 IMAD per point (SURVEY 8d, canonical c=16) x 2^20 points per launch",
-                    "share_of_step": acc_ms / ms_step}
+                    "share_of_step": acc_ms / ms_step_seq,
+                    "timed_in": "the sequential pass (one commit per call), CUDA events around the kernel on its stream"}
         extra["msm_whole_frac_of_imad_peak"] = IMAD_PER_POINT_MSM * N_POINTS / (ms_step * 1e-3) / imad_peak if world == 1 else None
 
     # ---- secondary headline: Fr NTT 2^22 (single GPU) and the C2 witness ----
@@ -334,6 +393,7 @@ def run_gpu(args):
         "config": {"workload": "C2 coeff-form commit: G1 MSM of a degree-(2^20-1) polynomial against a 2^20-point SRS per GPU",
                    "points_per_gpu": N_POINTS, "scalars": "full-width uniform Fr (splitmix64 seeds 42..49)", "srs": "s^i*G, secret seed 69",
                    "parallelism": "points sharded over %d GPU(s), all-gather of 192 B partials" % world,
+                   "steps": "K independent commits through the pipelined batch call (two work areas; tail of commit i overlaps commit i+1)",
                    "cache": "8 rotating 32 MiB scalar vectors (256 MiB) + 1.9 GB point table: inputs larger than L2"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": total_points / e2e_s, "unit": "points/s", "h2d_bytes_per_step": N_POINTS * 32, "d2h_bytes_per_step": 96,

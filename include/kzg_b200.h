@@ -110,6 +110,16 @@ KZGB_API int kzgb_msm_g1_jacobian(kzgb_srs* srs, const kzgb_fr* scalars, size_t 
 /* Device-pointer variant.  out_mode: 0 affine (96 B), 1 Jacobian (144 B), 2 raw XYZZ partial sum (192 B). */
 KZGB_API int kzgb_msm_g1_dev(kzgb_srs* srs, const void* d_scalars, size_t m, void* d_out, int out_mode, void* stream);
 /* Multi-GPU combine: sums `count` raw XYZZ partial sums (gathered from the ranks) into one point. */
+/* `count` commits against one SRS in one call (a prover committing to several polynomials; each item is
+ * coeff_form.rs:59-64).  Same results as `count` separate calls; consecutive MSMs are pipelined over two work
+ * areas so that one MSM's latency-bound tail overlaps the next one's copy, sort and accumulation.
+ * Host variant: scalars[i] -> ms[i] host scalars, out[i] affine.  Device variant: d_scalars is a HOST array of
+ * device pointers, d_out a device array of `count` results (out_mode 0 affine 96 B / 1 Jacobian 144 B / 2 XYZZ 192 B),
+ * ordered after and before the work on `stream`. */
+KZGB_API int kzgb_msm_g1_batch(kzgb_srs* srs, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
+                               kzgb_p1_affine* out);
+KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* srs, const void* const* d_scalars, const size_t* ms, size_t count,
+                                   void* d_out, int out_mode, void* stream);
 KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream);
 
 /* ---- Fr NTT: replaces the bodies of EvaluationDomain::fft (ft.rs:111-113) and ifft (ft.rs:115-140),

@@ -183,6 +183,24 @@ class SRS:
         check(lib().kzgb_msm_g1_dev(self._h, C.c_void_p(d_scalars), C.c_size_t(m), C.c_void_p(d_out),
                                     C.c_int(out_mode), C.c_void_p(stream)))
 
+    def msm_batch(self, scalars_list) -> np.ndarray:
+        """Several commits in one pipelined call: list of host scalar arrays -> [count, 12] affine points."""
+        arrs = [u64(a, (-1, 4)) for a in scalars_list]
+        count = len(arrs)
+        ptrs = (C.c_void_p * max(count, 1))(*[a.ctypes.data if len(a) else None for a in arrs])
+        ms = (C.c_size_t * max(count, 1))(*[len(a) for a in arrs])
+        out = np.zeros((count, 12), dtype=np.uint64)
+        check(lib().kzgb_msm_g1_batch(self._h, ptrs, ms, C.c_size_t(count), ptr(out)))
+        return out
+
+    def msm_batch_dev(self, d_scalars, ms, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+        """Device-resident batch: d_scalars = device pointers, ms = lengths, d_out = device array of results."""
+        count = len(d_scalars)
+        ptrs = (C.c_void_p * max(count, 1))(*[C.c_void_p(int(p)) for p in d_scalars])
+        lens = (C.c_size_t * max(count, 1))(*[int(m) for m in ms])
+        check(lib().kzgb_msm_g1_batch_dev(self._h, ptrs, lens, C.c_size_t(count), C.c_void_p(d_out), C.c_int(out_mode),
+                                          C.c_void_p(stream)))
+
     def close(self):
         if self._h is not None and _lib is not None and _initialised_device is not None:
             _lib.kzgb_srs_destroy(self._h)

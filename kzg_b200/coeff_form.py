@@ -42,6 +42,16 @@ class KZGProver:
             raise IndexError(f"range end index {n} out of range for slice of length {len(self._parameters)}")
         return self._parameters.srs.msm(polynomial.slice_coeffs())
 
+    def commit_many(self, polynomials) -> np.ndarray:
+        """`commit` (coeff_form.rs:59-64) of every polynomial in one pipelined call -> [count, 12] G1Affine.
+        Same results as calling `commit` in a loop; an extension of the reference API (a prover usually commits to
+        several polynomials against one SRS) that lets one MSM's tail overlap the next one's copy and accumulation."""
+        polynomials = list(polynomials)
+        for p in polynomials:
+            if p.num_coeffs() > len(self._parameters):
+                raise IndexError(f"range end index {p.num_coeffs()} out of range for slice of length {len(self._parameters)}")
+        return self._parameters.srs.msm_batch([p.slice_coeffs() for p in polynomials])
+
     def create_witness(self, polynomial: Polynomial, point) -> np.ndarray:
         """coeff_form.rs:66-81.  Raises PointNotOnPolynomial when (X - x) does not divide p - y."""
         x, y = point

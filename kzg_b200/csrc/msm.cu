@@ -679,6 +679,8 @@ void srs_free(kzgb_srs* s) {
     if (!s) return;
     if (s->table) cudaFree(s->table);
     if (s->work) cudaFree(s->work);
+    for (int k = 0; k < 2; k++)
+        if (s->pipe_work[k]) cudaFree(s->pipe_work[k]);
     delete s;
 }
 
@@ -746,7 +748,8 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
 
 // Runs the MSM of the first m table points against d_scalars (device, Montgomery Fr).
 // The XYZZ result is left at *d_result_xyzz (inside the SRS work area).
-int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, const XYZZ** d_result_xyzz) {
+int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, const XYZZ** d_result_xyzz, int slot,
+            cudaStream_t tail_stream, cudaEvent_t handoff) {
     if (m > s->n) {
         set_error("msm: %zu scalars but the SRS holds %zu points", m, s->n);
         return KZGB_ERR_INVALID_ARG;
@@ -754,21 +757,28 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     MsmPlan p;
     int st = msm_plan(s, m ? m : 1, p);
     if (st) return st;
-    if (p.bytes > s->work_bytes) {
-        if (s->work) {
+    void*& work = slot < 0 ? s->work : s->pipe_work[slot & 1];
+    size_t& work_bytes = slot < 0 ? s->work_bytes : s->pipe_work_bytes[slot & 1];
+    if (p.bytes > work_bytes) {
+        if (work) {
             KZG_CUDA(cudaStreamSynchronize(stream));
-            cudaFree(s->work);
-            s->work = nullptr;
-            s->work_bytes = 0;
+            if (tail_stream) KZG_CUDA(cudaStreamSynchronize(tail_stream));
+            cudaFree(work);
+            work = nullptr;
+            work_bytes = 0;
         }
-        KZG_CUDA(cudaMalloc(&s->work, p.bytes));
-        s->work_bytes = p.bytes;
+        KZG_CUDA(cudaMalloc(&work, p.bytes));
+        work_bytes = p.bytes;
     }
-    char* w = (char*)s->work;
+    char* w = (char*)work;
     XYZZ* result = (XYZZ*)(w + p.off_result);
     *d_result_xyzz = result;
     if (m == 0) {
         KZG_CUDA(cudaMemsetAsync(result, 0, sizeof(XYZZ), stream));
+        if (tail_stream && tail_stream != stream) {
+            KZG_CUDA(cudaEventRecord(handoff, stream));
+            KZG_CUDA(cudaStreamWaitEvent(tail_stream, handoff, 0));
+        }
         return KZGB_OK;
     }
     uint32_t* keys0 = (uint32_t*)(w + p.off_keys0);
@@ -800,6 +810,11 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
                                                                       buckets, partials, meta, p.nthreads);
     KZG_LAUNCHED();
     stage_end(ST_MSM_ACCUMULATE, stream);
+    if (tail_stream && tail_stream != stream) {  // pipelined batch: the tail goes to its own (high-priority) stream
+        KZG_CUDA(cudaEventRecord(handoff, stream));
+        KZG_CUDA(cudaStreamWaitEvent(tail_stream, handoff, 0));
+        stream = tail_stream;
+    }
     stage_begin(ST_MSM_FIXUP, stream);
     {
         const XYZZ* pin = partials;

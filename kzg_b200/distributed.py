@@ -49,6 +49,14 @@ class CudaOps:
 
     device_type = "cuda"
 
+    def msm_partial_many(self, srs: _ffi.SRS, scalars_list, out_xyzz: torch.Tensor) -> None:
+        srs.msm_batch_dev([t.data_ptr() for t in scalars_list], [t.shape[0] for t in scalars_list], out_xyzz.data_ptr(), 2,
+                          torch.cuda.current_stream().cuda_stream)
+
+    def msm_affine_many(self, srs: _ffi.SRS, scalars_list, out_affine: torch.Tensor) -> None:
+        srs.msm_batch_dev([t.data_ptr() for t in scalars_list], [t.shape[0] for t in scalars_list], out_affine.data_ptr(), 0,
+                          torch.cuda.current_stream().cuda_stream)
+
     def msm_partial(self, srs: _ffi.SRS, scalars: torch.Tensor, out_xyzz: torch.Tensor) -> None:
         srs.msm_dev(scalars.data_ptr(), scalars.shape[0], out_xyzz.data_ptr(), 2,
                     torch.cuda.current_stream().cuda_stream)
@@ -73,6 +81,34 @@ def sharded_msm(srs_shard, scalars_shard: torch.Tensor, ops=None, group=None) ->
         gathered = partial
     out = torch.zeros(12, dtype=torch.int64, device=dev)
     ops.g1_combine(gathered, world, out)
+    return out
+
+
+def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None) -> torch.Tensor:
+    """`sharded_msm` for K polynomials at once: the K local MSMs run through the pipelined batch entry point, the K
+    partials travel in ONE all-gather (G x K x 192 bytes) and are combined on every rank -> int64[K, 12]."""
+    ops = ops or CudaOps()
+    k = len(scalars_shards)
+    dev = scalars_shards[0].device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    out = torch.zeros((k, 12), dtype=torch.int64, device=dev)
+    if world == 1 and hasattr(ops, "msm_affine_many"):
+        ops.msm_affine_many(srs_shard, scalars_shards, out)
+        return out
+    partials = torch.zeros((k, 24), dtype=torch.int64, device=dev)
+    if hasattr(ops, "msm_partial_many"):
+        ops.msm_partial_many(srs_shard, scalars_shards, partials)
+    else:
+        for i, sc in enumerate(scalars_shards):
+            ops.msm_partial(srs_shard, sc, partials[i])
+    if world > 1:
+        gathered = torch.empty((world, k, 24), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), partials.view(-1), group=group)
+        per_item = gathered.transpose(0, 1).contiguous()      # [k][world][24]
+    else:
+        per_item = partials.view(k, 1, 24)
+    for i in range(k):
+        ops.g1_combine(per_item[i].reshape(-1), world, out[i])
     return out
 
 

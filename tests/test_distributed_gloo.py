@@ -158,6 +158,11 @@ def _worker(rank, world, port, q):
         out = kd.sharded_msm(gs[lo:hi], _from_np(sc[lo:hi]), ops=OracleMsmOps(cpu))
         expect = cpu.g1_to_affine(cpu.msm_g1(gs, sc, 1))[0]
         ok_msm = bool((_to_np(out) == expect).all())
+        # ---- K polynomials at once: one all-gather of K partials ----
+        sc2 = cpu.fr_stream(43, n)
+        outs = kd.sharded_msm_many(gs[lo:hi], [_from_np(sc[lo:hi]), _from_np(sc2[lo:hi])], ops=OracleMsmOps(cpu))
+        ok_msm = ok_msm and bool((_to_np(outs[0]) == expect).all())
+        ok_msm = ok_msm and bool((_to_np(outs[1]) == cpu.g1_to_affine(cpu.msm_g1(gs, sc2, 1))[0]).all())
         # ---- four-step NTT, forward and inverse ----
         log_n = 8
         vec = cpu.fr_stream(5, 1 << log_n)

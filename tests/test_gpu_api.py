@@ -42,6 +42,19 @@ def test_basic(params, golden):
         prover.commit(kzg.Polynomial.from_ints(list(range(1, 18))))
 
 
+def test_commit_many_equals_commit_loop(params):
+    """commit_many (pipelined batch behind kzgb_msm_g1_batch) == [commit(p) for p in ...], incl. padded degrees."""
+    prover = kzg.KZGProver(params)
+    polys = [kzg.Polynomial.from_ints(O.fr_stream(50 + i, k)) for i, k in enumerate((16, 1, 7, 16, 3))]
+    polys.append(kzg.Polynomial(scalar.fr_vec(O.fr_stream_u64(42, 6) + [0] * 10), 15))
+    many = prover.commit_many(polys)
+    for p, c in zip(polys, many):
+        assert (prover.commit(p) == c).all()
+    assert (many[0] == point(ev(O.fr_stream(50, 16), SECRET))).all()
+    with pytest.raises(IndexError):
+        prover.commit_many([polys[0], kzg.Polynomial.from_ints(list(range(1, 18)))])
+
+
 def test_modify_single_coeff(params):
     """coeff_form.rs:295-311."""
     prover = kzg.KZGProver(params)
