@@ -121,6 +121,9 @@ KZGB_API int kzgb_msm_g1_batch(kzgb_srs* srs, const kzgb_fr* const* scalars, con
 KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* srs, const void* const* d_scalars, const size_t* ms, size_t count,
                                    void* d_out, int out_mode, void* stream);
 KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream);
+/* K polynomials at once: d_partials = all-gathered [count ranks][items][192 B]; d_out = `items` results */
+KZGB_API int kzgb_g1_combine_batch_dev(const void* d_partials, uint32_t count, uint32_t items, void* d_out, int out_mode,
+                                       void* stream);
 
 /* ---- Fr NTT: replaces the bodies of EvaluationDomain::fft (ft.rs:111-113) and ifft (ft.rs:115-140),
  * i.e. best_fft/serial_fft/parallel_fft (ft.rs:274-387).  In place over 2^log_n Montgomery-form elements,

@@ -218,6 +218,11 @@ def g1_combine_dev(d_partials: int, count: int, d_out: int, out_mode: int = 0, s
                                     C.c_void_p(stream)))
 
 
+def g1_combine_batch_dev(d_partials: int, count: int, items: int, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+    check(lib().kzgb_g1_combine_batch_dev(C.c_void_p(d_partials), C.c_uint32(count), C.c_uint32(items), C.c_void_p(d_out),
+                                          C.c_int(out_mode), C.c_void_p(stream)))
+
+
 def srs_generate(kind: int, secret, total: int, first: int = 0, count: int | None = None, window_bits: int = 0) -> SRS:
     """Synthetic SRS from a known secret, built on the device.  kind 0: s^i*G (lib.rs:38-46);
     kind 1: Lagrange L_i(s)*G (eval_form.rs:254-280)."""

@@ -283,4 +283,24 @@ KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d
     return msm_finish((const XYZZ*)d, d_out, out_mode, st);
 }
 
+
+// Batched combine (K polynomials at once): d_partials is the all-gathered [count ranks][items][192 B] array;
+// d_out receives `items` results in out_mode layout.  One block per item, so the K affine conversions run side by side.
+KZGB_API int kzgb_g1_combine_batch_dev(const void* d_partials, uint32_t count, uint32_t items, void* d_out, int out_mode,
+                                       void* stream) {
+    KZG_REQUIRE_INIT();
+    KZG_LOCK();
+    if (!d_partials || !d_out || count == 0 || out_mode < 0 || out_mode > 2) {
+        set_error("kzgb_g1_combine_batch_dev: bad argument");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    if (items == 0) return KZGB_OK;
+    cudaStream_t st = pick_stream(stream);
+    char* d = (char*)scratch_reserve((size_t)items * 192);
+    if (!d) return KZGB_ERR_CUDA;
+    int rc = msm_combine(d_partials, count, d, st, items);
+    if (rc) return rc;
+    return msm_finish((const XYZZ*)d, d_out, out_mode, st, items);
+}
+
 }  // extern "C"

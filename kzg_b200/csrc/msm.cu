@@ -526,29 +526,32 @@ __global__ void __launch_bounds__(WS_THREADS) msm_reduce_final_kernel(const XYZZ
 
 // K6: result conversion.  mode 0: affine (blst_p1_affine), 1: Jacobian (blst_p1), 2: raw XYZZ
 __global__ void msm_finish_kernel(const XYZZ* __restrict__ in, void* __restrict__ out, int mode) {
-    if (threadIdx.x || blockIdx.x) return;
-    XYZZ p = ld_xyzz(in);
+    if (threadIdx.x) return;
+    // one block per result (gridDim.x = 1 everywhere except the batched multi-GPU combine)
+    XYZZ p = ld_xyzz(in + blockIdx.x);
     if (mode == 0) {
         Affine a = xyzz_to_affine(p);
-        stg_affine((Affine*)out, a);
+        stg_affine((Affine*)out + blockIdx.x, a);
     } else if (mode == 1) {
         Jacobian j = xyzz_to_jacobian(p);
-        Jacobian* o = (Jacobian*)out;
+        Jacobian* o = (Jacobian*)out + blockIdx.x;
         stg_fq(&o->x, j.x); stg_fq(&o->y, j.y); stg_fq(&o->z, j.z);
     } else {
-        st_xyzz((XYZZ*)out, p);
+        st_xyzz((XYZZ*)out + blockIdx.x, p);
     }
 }
 
 // sum of `count` XYZZ/Jacobian partial results (multi-GPU combine) -> finish
-__global__ void msm_combine_kernel(const XYZZ* __restrict__ in, uint32_t count, XYZZ* __restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void msm_combine_kernel(const XYZZ* __restrict__ in, uint32_t count, XYZZ* __restrict__ out,
+                                   uint32_t rank_stride) {
+    if (threadIdx.x) return;
+    // block b sums in[g * rank_stride + b], g < count (one block per item of a batch; a single item has stride 1)
     XYZZ acc = XYZZ::inf();
-    for (uint32_t i = 0; i < count; i++) {
-        XYZZ q = ld_xyzz(&in[i]);
+    for (uint32_t g = 0; g < count; g++) {
+        XYZZ q = ld_xyzz(&in[(size_t)g * rank_stride + blockIdx.x]);
         xyzz_add(acc, q);
     }
-    st_xyzz(out, acc);
+    st_xyzz(out + blockIdx.x, acc);
 }
 
 // --------------------------------------------------------------------------
@@ -891,15 +894,16 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     return KZGB_OK;
 }
 
-int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream) {
-    msm_finish_kernel<<<1, 32, 0, stream>>>(d_xyzz, d_out, mode);
+int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream, uint32_t items) {
+    msm_finish_kernel<<<items, 32, 0, stream>>>(d_xyzz, d_out, mode);
     KZG_LAUNCHED();
     stage_end(ST_MSM_FINISH, stream);
     return KZGB_OK;
 }
 
-int msm_combine(const void* d_partials_xyzz, uint32_t count, void* d_out_xyzz, cudaStream_t stream) {
-    msm_combine_kernel<<<1, 32, 0, stream>>>((const XYZZ*)d_partials_xyzz, count, (XYZZ*)d_out_xyzz);
+int msm_combine(const void* d_partials_xyzz, uint32_t count, void* d_out_xyzz, cudaStream_t stream, uint32_t items) {
+    msm_combine_kernel<<<items, 32, 0, stream>>>((const XYZZ*)d_partials_xyzz, count, (XYZZ*)d_out_xyzz,
+                                                 items > 1 ? items : 1);
     KZG_LAUNCHED();
     return KZGB_OK;
 }

@@ -65,6 +65,11 @@ class CudaOps:
         _ffi.g1_combine_dev(partials.data_ptr(), count, out_affine.data_ptr(), 0,
                             torch.cuda.current_stream().cuda_stream)
 
+    def g1_combine_many(self, gathered: torch.Tensor, count: int, items: int, out_affine: torch.Tensor) -> None:
+        """gathered: [count ranks][items][24] -> out_affine [items][12], one launch pair for all items."""
+        _ffi.g1_combine_batch_dev(gathered.data_ptr(), count, items, out_affine.data_ptr(), 0,
+                                  torch.cuda.current_stream().cuda_stream)
+
 
 def sharded_msm(srs_shard, scalars_shard: torch.Tensor, ops=None, group=None) -> torch.Tensor:
     """commit over a point-sharded SRS: every rank passes ITS slice of the scalars (aligned with its SRS shard)
@@ -104,11 +109,14 @@ def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None) -> torch.T
     if world > 1:
         gathered = torch.empty((world, k, 24), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gathered.view(-1), partials.view(-1), group=group)
-        per_item = gathered.transpose(0, 1).contiguous()      # [k][world][24]
     else:
-        per_item = partials.view(k, 1, 24)
-    for i in range(k):
-        ops.g1_combine(per_item[i].reshape(-1), world, out[i])
+        gathered = partials.view(1, k, 24)
+    if hasattr(ops, "g1_combine_many"):
+        ops.g1_combine_many(gathered, world, k, out)
+    else:
+        per_item = gathered.transpose(0, 1).contiguous()      # [k][world][24]
+        for i in range(k):
+            ops.g1_combine(per_item[i].reshape(-1), world, out[i])
     return out
 
 

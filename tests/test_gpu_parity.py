@@ -157,6 +157,16 @@ def test_msm_batch_pipelined_matches_single_calls(gpu, cpu):
         gpu.g1_combine_dev(xyzz[i].data_ptr(), 1, aff.data_ptr(), 0, st)
         torch.cuda.synchronize()
         assert (aff.cpu().numpy().view(np.uint64) == singles[i]).all()
+    # batched multi-GPU combine: pretend 3 ranks gathered [3][K][24] partials -> out[i] = sum over ranks
+    K = len(polys)
+    gathered = torch.stack([xyzz, xyzz.roll(1, 0), xyzz.roll(2, 0)]).contiguous()
+    outs = torch.zeros((K, 12), dtype=torch.int64, device="cuda")
+    gpu.g1_combine_batch_dev(gathered.data_ptr(), 3, K, outs.data_ptr(), 0, st)
+    torch.cuda.synchronize()
+    J = lambda a: np.concatenate([a, np.array(O.fq_to_mont_limbs(1), dtype=np.uint64)]) if a.any() else np.zeros(18, dtype=np.uint64)
+    for i in range(K):
+        e = cpu.g1_add(cpu.g1_add(J(singles[i]), J(singles[(i - 1) % K])), J(singles[(i - 2) % K]))
+        assert (outs[i].cpu().numpy().view(np.uint64) == cpu.g1_to_affine(e)[0]).all()
     with pytest.raises(gpu.KZGBackendError):
         srs.msm_batch([np.zeros((n + 1, 4), dtype=np.uint64)])
     # host mirror
