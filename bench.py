@@ -308,6 +308,8 @@ def run_gpu(args):
                     "unit": "TIMAD/s (32x32->64 multiply-adds)", "frac": achieved / imad_peak, "traffic": traffic,
                     "peak_source": "measured live: kzgb_microbench mode 3 (dense independent IMAD.WIDE.U32 chains)",
                     "algorithmic_work": "16 windows x 3000 IMAD per point (SURVEY 8d, canonical c=16) x 2^20 points per launch",
+                    "executed_work": "%d windows x (8 x 300 + 2 x 222) IMAD actually issued per point at c = %d" % (-(-256 // srs.window_bits), srs.window_bits),
+                    "frac_executed": (-(-256 // srs.window_bits)) * 2844 * N_POINTS / (acc_ms * 1e-3) / imad_peak,
                     "share_of_step": acc_ms / ms_step_seq,
                     "timed_in": "the sequential pass (one commit per call), CUDA events around the kernel on its stream"}
         extra["msm_whole_frac_of_imad_peak"] = IMAD_PER_POINT_MSM * N_POINTS / (ms_step * 1e-3) / imad_peak if world == 1 else None

@@ -101,6 +101,20 @@ public:
         check(kzgb_msm_g1(parameters_.handle(), p.slice_coeffs(), p.num_coeffs(), &out), "kzgb_msm_g1");
         return out;
     }
+    // commit (coeff_form.rs:59-64) of several polynomials in one pipelined call (kzgb_msm_g1_batch): same results as a
+    // loop of commit(); the tail of one MSM overlaps the copy / sort / accumulation of the next
+    std::vector<G1Affine> commit_many(const std::vector<const Polynomial*>& ps) const {
+        std::vector<const kzgb_fr*> ptrs;
+        std::vector<size_t> lens;
+        for (const Polynomial* p : ps) {
+            if (p->num_coeffs() > parameters_.len()) throw std::runtime_error("range end index out of range for slice");
+            ptrs.push_back(p->slice_coeffs());
+            lens.push_back(p->num_coeffs());
+        }
+        std::vector<G1Affine> out(ps.size());
+        check(kzgb_msm_g1_batch(parameters_.handle(), ptrs.data(), lens.data(), ps.size(), out.data()), "kzgb_msm_g1_batch");
+        return out;
+    }
     Result<G1Affine> create_witness(const Polynomial& p, const Scalar& x, const Scalar& y) const {  // coeff_form.rs:66-81
         G1Affine out;
         int st = kzgb_witness_coeff(parameters_.handle(), p.slice_coeffs(), p.num_coeffs(), &x, &y, &out);

@@ -23,6 +23,7 @@ extern "C" {
     pub fn kzgb_srs_destroy(srs: *mut kzgb_srs) -> c_int;
     pub fn kzgb_msm_g1_jacobian(srs: *mut kzgb_srs, scalars: *const Scalar, m: usize, out: *mut G1Projective) -> c_int;
     pub fn kzgb_msm_g1(srs: *mut kzgb_srs, scalars: *const Scalar, m: usize, out: *mut G1Affine) -> c_int;
+    pub fn kzgb_msm_g1_batch(srs: *mut kzgb_srs, scalars: *const *const Scalar, ms: *const usize, count: usize, out: *mut G1Affine) -> c_int;
     pub fn kzgb_ntt_fr(inout: *mut Scalar, log_n: u32, inverse: c_int) -> c_int;
     pub fn kzgb_divide_linear(p: *const Scalar, n: usize, x: *const Scalar, y: *const Scalar, q_out: *mut Scalar, rem_out: *mut Scalar) -> c_int;
     pub fn kzgb_witness_coeff(srs: *mut kzgb_srs, p: *const Scalar, n: usize, x: *const Scalar, y: *const Scalar, out: *mut G1Affine) -> c_int;

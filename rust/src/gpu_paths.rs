@@ -13,6 +13,17 @@ pub fn multi_exp(srs: &Srs, scalars: &[Scalar]) -> G1Projective {
     out
 }
 
+/// `commit` (coeff_form.rs:59-64) of several polynomials in one call: an addition to the reference API
+/// (`KZGProver::commit_many`), same results as a loop of `commit`.  The library pipelines the MSMs over two work
+/// areas so that the latency-bound tail of one overlaps the copy / sort / accumulation of the next.
+pub fn multi_exp_many(srs: &Srs, polys: &[&[Scalar]]) -> Vec<G1Affine> {
+    let ptrs: Vec<*const Scalar> = polys.iter().map(|p| p.as_ptr()).collect();
+    let lens: Vec<usize> = polys.iter().map(|p| p.len()).collect();
+    let mut out = vec![G1Affine::default(); polys.len()];
+    ffi::check(unsafe { ffi::kzgb_msm_g1_batch(srs.raw(), ptrs.as_ptr(), lens.as_ptr(), polys.len(), out.as_mut_ptr()) }, "kzgb_msm_g1_batch");
+    out
+}
+
 /// Body of `best_fft(a, omega, log_n)` for the domain's own omega / omegainv — ft.rs:274-288 as called from
 /// `EvaluationDomain::fft` (ft.rs:112) and `ifft` (ft.rs:116; the `* minv` loop at :118-139 is fused, so `ifft`
 /// calls this with `inverse = true` and drops its scaling loop).
