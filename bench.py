@@ -42,45 +42,64 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """Clocks / throttle reasons DURING the timed region: ONE `nvidia-smi -lms` poller per rank, started before the
+    warm-up (so its start-up cost -- NVML initialisation touches every GPU of the box -- is outside the timed region)
+    and killed at the end, as the profiling recipe prescribes; samples are time-stamped and those inside
+    [begin(), end()] are summarised."""
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self._stop = threading.Event()
-        self._t = None
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def _run(self):
+    def __init__(self, index, period_ms=100):
+        self.rows = []          # (monotonic time, [fields])
+        self.t0 = self.t1 = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.15)
-
-    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
-        return self
 
-    def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+    def _run(self):
+        if not self.proc:
+            return
+        for line in self.proc.stdout:
+            f = [c.strip() for c in line.split(",")]
+            if len(f) >= 6:
+                self.rows.append((time.monotonic(), f))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
+
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k] == "Active" for r in self.rows)]
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        inside = [f for (t, f) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        note = None
+        if not inside and self.rows and self.t0 is not None:   # region shorter than the polling period: nearest sample
+            inside = [min(self.rows, key=lambda r: abs(r[0] - (self.t0 + (self.t1 or self.t0)) / 2))[1]]
+            note = "timed region shorter than the polling period: nearest sample"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(int(r[0]) for r in inside if r[0].isdigit())
+        mx = [int(r[1]) for r in inside if r[1].isdigit()]
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[2 + k] == "Active" for r in inside)]
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+               "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_run(steps, warmup, sample_log, gs_jac=None, scalars=None):
@@ -146,6 +165,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     _ffi.init(local)
     stream = torch.cuda.current_stream().cuda_stream
+    clk = ClockSampler(local)   # one poller, started before the warm-up
 
     def barrier():
         if world > 1:
@@ -194,6 +214,7 @@ def run_gpu(args):
     for i in range(args.warmup):
         step(i)
     steps_pipelined(0, max(args.warmup, 3))
+    steps_pipelined(0, args.steps)   # same batch size as the timed call: arenas and NCCL buffers are at their final size
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -211,14 +232,21 @@ def run_gpu(args):
     _ffi.profile_enable(False)
     # ---- headline pass: the same K commits through the pipelined batch ----
     launches0 = _ffi.launch_count()
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        outs = steps_pipelined(args.warmup, args.steps)
-        e1.record()
-        barrier()
+    barrier()
+    clk.begin()
+    e0.record()
+    outs = steps_pipelined(args.warmup, args.steps)
+    e1.record()
+    barrier()
+    clk.end()
     launches = _ffi.launch_count() - launches0
+    my_ms = e0.elapsed_time(e1) / args.steps
     ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    per_rank_ms = [my_ms]
+    if world > 1:
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([my_ms], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(x.item()) for x in tl]
     value = total_points / (ms_step * 1e-3)
     if rank == 0 and world == 1:   # the pipelined results are the sequential ones: step `warmup` again, one call
         chk = step(args.warmup)
@@ -238,9 +266,10 @@ def run_gpu(args):
     def e2e_steps(count):
         if world == 1:   # the public host-pointer call: K commits, each with its own H2D and D2H
             return srs.msm_batch([host_views[i % 2] for i in range(count)])
-        ds = [host_polys[i % 2].to(dev, non_blocking=True) for i in range(count)]
-        return kd.sharded_msm_many(srs, ds, ops).cpu()
+        # N > 1: host scalars in (copies pipelined with the MSMs), partials all-gathered, results read back
+        return kd.sharded_msm_many(srs, [host_views[i % 2] for i in range(count)], ops, device=dev).cpu()
     e2e_steps(2)
+    e2e_steps(args.steps)
     barrier()
     t0 = time.perf_counter()
     e2e_out = e2e_steps(args.steps)
@@ -282,6 +311,7 @@ def run_gpu(args):
                 "variants with the single-GPU transform: scripts/dist_check.py, profiles/r01g_dist_check_fused_n*.log"}
         del slab, work4
 
+    clk.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,7 +319,7 @@ def run_gpu(args):
     stage_ms = {k: v[0] / v[1] for k, v in prof.items()}
     acc_ms = stage_ms.get("msm_accumulate")
     extra = {"stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}, "window_bits": srs.window_bits,
-             "srs_table_bytes": srs.device_bytes,
+             "srs_table_bytes": srs.device_bytes, "ms_per_step_by_rank": [round(x, 4) for x in per_rank_ms],
              "sequential": {"ms_per_step": ms_step_seq, "value": total_points / (ms_step_seq * 1e-3),
                             "e2e_ms_per_step": e2e_seq_s * 1e3 if e2e_seq_s else None,
                             "e2e_value": N_POINTS / e2e_seq_s if e2e_seq_s else None,

@@ -120,6 +120,9 @@ KZGB_API int kzgb_msm_g1_batch(kzgb_srs* srs, const kzgb_fr* const* scalars, con
                                kzgb_p1_affine* out);
 KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* srs, const void* const* d_scalars, const size_t* ms, size_t count,
                                    void* d_out, int out_mode, void* stream);
+/* host scalars in, device results out (multi-GPU commit from host buffers); returns when the batch is complete */
+KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* srs, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
+                                   void* d_out, int out_mode, void* stream);
 KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream);
 /* K polynomials at once: d_partials = all-gathered [count ranks][items][192 B]; d_out = `items` results */
 KZGB_API int kzgb_g1_combine_batch_dev(const void* d_partials, uint32_t count, uint32_t items, void* d_out, int out_mode,

@@ -201,6 +201,15 @@ class SRS:
         check(lib().kzgb_msm_g1_batch_dev(self._h, ptrs, lens, C.c_size_t(count), C.c_void_p(d_out), C.c_int(out_mode),
                                           C.c_void_p(stream)))
 
+    def msm_batch_h2d(self, scalars_list, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+        """Host scalar arrays in, device results out (pipelined copies); returns when the batch is complete."""
+        arrs = [u64(a, (-1, 4)) for a in scalars_list]
+        count = len(arrs)
+        ptrs = (C.c_void_p * max(count, 1))(*[a.ctypes.data if len(a) else None for a in arrs])
+        lens = (C.c_size_t * max(count, 1))(*[len(a) for a in arrs])
+        check(lib().kzgb_msm_g1_batch_h2d(self._h, ptrs, lens, C.c_size_t(count), C.c_void_p(d_out), C.c_int(out_mode),
+                                          C.c_void_p(stream)))
+
     def close(self):
         if self._h is not None and _lib is not None and _initialised_device is not None:
             _lib.kzgb_srs_destroy(self._h)

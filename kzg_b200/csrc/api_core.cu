@@ -42,7 +42,10 @@ void* scratch_reserve(size_t bytes) {
         c.scratch = nullptr;
         c.scratch_bytes = 0;
     }
+    // never smaller than 4 MiB: growing the arena synchronises the device and goes through cudaFree/cudaMalloc
+    // (measured: up to 0.5 s with several processes on one box), so tiny requests must not trigger it repeatedly
     size_t want = bytes + (bytes >> 2);
+    if (want < ((size_t)4 << 20)) want = (size_t)4 << 20;
     cudaError_t e = cudaMalloc(&c.scratch, want);
     if (e != cudaSuccess) {
         cuda_fail(e, "cudaMalloc(scratch)", __FILE__, __LINE__);

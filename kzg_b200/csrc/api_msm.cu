@@ -1,5 +1,9 @@
 // api_msm.cu -- C ABI: SRS handles and the G1 MSM entry points.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <vector>
 
 #include "common.cuh"
 #include "ec.cuh"
@@ -133,14 +137,19 @@ KZGB_API int kzgb_msm_g1_jacobian(kzgb_srs* s, const kzgb_fr* scalars, size_t m,
 // ---- pipelined batch of MSMs against one SRS (commit to many polynomials) -------------------------------------
 // A single MSM ends in a latency-bound tail (fix-up levels, bucket reduction, affine conversion: ~1.4 ms of ~7 ms at
 // 2^20 on small grids) and, through the host-pointer entry point, starts with a 32 MiB host-to-device copy.  In a
-// batch, consecutive MSMs alternate between two work areas and two stream pairs: the copy, digit extraction, sort
-// and accumulation of MSM i+1 run on a low-priority stream while the tail of MSM i runs on a high-priority stream,
-// so the tail's few blocks slot in as accumulation blocks retire.  Results are identical to `count` separate calls.
+// batch, consecutive MSMs alternate between two work areas:
+//   * ONE low-priority "heavy" stream runs digits -> sort -> accumulation of every item in order (two accumulations
+//     sharing the machine would only fight for the same pipe),
+//   * the tail of item i runs on the high-priority stream of its slot, so its few blocks slot in while the heavy
+//     stream is already accumulating item i+1,
+//   * a copy stream moves item i+1's scalars while item i computes.
+// Events hand the slot (staging + work area) back once the tail of item i is done; item i+2 waits for it.
+// Results are identical to `count` separate calls.
 namespace {
 struct MsmPipe {
     bool ready = false;
-    cudaStream_t main_s[2], tail_s[2];
-    cudaEvent_t handoff[2], done[2];
+    cudaStream_t heavy, copy, tail_s[2];
+    cudaEvent_t handoff[2], done[2], staged[2];
     void* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes[2] = {0, 0};
     void* d_out = nullptr;      // count x 192 B device results (host variant)
@@ -154,11 +163,13 @@ int pipe_init() {
     if (g_pipe.ready) return KZGB_OK;
     int lo = 0, hi = 0;  // lo = least priority (numerically greatest), hi = greatest priority
     KZG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.heavy, cudaStreamNonBlocking, lo));
+    KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.copy, cudaStreamNonBlocking, lo));
     for (int k = 0; k < 2; k++) {
-        KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.main_s[k], cudaStreamNonBlocking, lo));
         KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.tail_s[k], cudaStreamNonBlocking, hi));
         KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.handoff[k], cudaEventDisableTiming));
         KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.done[k], cudaEventDisableTiming));
+        KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.staged[k], cudaEventDisableTiming));
     }
     g_pipe.ready = true;
     return KZGB_OK;
@@ -166,75 +177,131 @@ int pipe_init() {
 
 size_t out_size(int mode) { return mode == 0 ? sizeof(kzgb_p1_affine) : (mode == 1 ? sizeof(kzgb_p1) : 192); }
 
-// scalars[i]: host (on_device = 0) or device pointers; out: host or device array of `count` results, out_size(mode)
-// bytes apart.  `after`: a stream whose already-enqueued work the batch must wait for (device variant), or nullptr.
-int msm_batch(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int on_device,
-              cudaStream_t after) {
-    int st = pipe_init();
-    if (st) return st;
+int pipe_drain(int rc) {
+    cudaStream_t all[4] = {g_pipe.copy, g_pipe.heavy, g_pipe.tail_s[0], g_pipe.tail_s[1]};
+    for (cudaStream_t st : all) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == KZGB_OK && e != cudaSuccess) rc = cuda_fail(e, "sync(batch)", __FILE__, __LINE__);
+    }
+    return rc;
+}
+
+// where: bit 0 = scalars[i] are device pointers (else host), bit 1 = `out` is a device array (else host); results are
+// out_size(mode) bytes apart.  `after`: a stream whose already-enqueued work the batch must wait for and which
+// receives the completion (device output), or nullptr.
+// KZGB_PIPE_DEBUG=1: per-item timeline on stderr (host enqueue time, GPU time of the hand-off and of completion)
+struct PipeDbg { double host_ms; cudaEvent_t acc_done, done; };
+static std::vector<PipeDbg> g_dbg;
+static cudaEvent_t g_dbg_start = nullptr;
+static bool pipe_debug() { static int v = -1; if (v < 0) { const char* e = getenv("KZGB_PIPE_DEBUG"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
+int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int where,
+                  cudaStream_t after) {
+    const bool sc_dev = (where & 1) != 0, out_dev = (where & 2) != 0;
     const size_t osz = out_size(mode);
-    if (!on_device && count) {
-        if (g_pipe.out_bytes < count * 192) {
-            if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; }
-            KZG_CUDA(cudaMalloc(&g_pipe.d_out, count * 192));
-            KZG_CUDA(cudaMallocHost(&g_pipe.h_out, count * 192));
-            g_pipe.out_bytes = count * 192;
-        }
+    const bool dbg = pipe_debug();
+    double h0 = now_ms();
+    if (dbg) {
+        g_dbg.clear();
+        cudaEventCreate(&g_dbg_start);
+        cudaEventRecord(g_dbg_start, g_pipe.heavy);
     }
-    cudaEvent_t start_ev = nullptr;
-    if (after) {
-        KZG_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
-        KZG_CUDA(cudaEventRecord(start_ev, after));
+    if (!out_dev && count && g_pipe.out_bytes < count * 192) {
+        if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; }
+        KZG_CUDA(cudaMalloc(&g_pipe.d_out, count * 192));
+        KZG_CUDA(cudaMallocHost(&g_pipe.h_out, count * 192));
+        g_pipe.out_bytes = count * 192;
     }
-    int rc = KZGB_OK;
-    for (size_t i = 0; i < count && rc == KZGB_OK; i++) {
+    for (size_t i = 0; i < count; i++) {
         const int k = (int)(i & 1);
-        cudaStream_t ms_ = g_pipe.main_s[k], ts_ = g_pipe.tail_s[k];
-        if (i < 2 && start_ev) KZG_CUDA(cudaStreamWaitEvent(ms_, start_ev, 0));
-        // the work area and staging of this slot are free once the tail of MSM i-2 has finished
-        if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(ms_, g_pipe.done[k], 0));
+        cudaStream_t ts_ = g_pipe.tail_s[k];
         const size_t m = ms[i];
-        if (m > s->n) { set_error("kzgb_msm_g1_batch: item %zu has %zu scalars > %zu SRS points", i, m, s->n); rc = KZGB_ERR_INVALID_ARG; break; }
+        if (m > s->n) {
+            set_error("kzgb_msm_g1_batch: item %zu has %zu scalars > %zu SRS points", i, m, s->n);
+            return KZGB_ERR_INVALID_ARG;
+        }
         const void* d_sc = scalars[i];
-        if (!on_device) {
+        if (!sc_dev) {
             const size_t bytes = m * sizeof(kzgb_fr);
             if (g_pipe.stage_bytes[k] < bytes) {
-                KZG_CUDA(cudaStreamSynchronize(ms_));
-                KZG_CUDA(cudaStreamSynchronize(ts_));
+                int rc = pipe_drain(KZGB_OK);
+                if (rc) return rc;
                 if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
                 g_pipe.d_stage[k] = nullptr;
                 g_pipe.stage_bytes[k] = 0;
                 KZG_CUDA(cudaMalloc(&g_pipe.d_stage[k], bytes));
                 g_pipe.stage_bytes[k] = bytes;
             }
-            if (m) KZG_CUDA(cudaMemcpyAsync(g_pipe.d_stage[k], scalars[i], bytes, cudaMemcpyHostToDevice, ms_));
+            // the staging buffer of this slot is free once the tail of item i-2 has finished
+            if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.done[k], 0));
+            if (m) KZG_CUDA(cudaMemcpyAsync(g_pipe.d_stage[k], scalars[i], bytes, cudaMemcpyHostToDevice, g_pipe.copy));
+            KZG_CUDA(cudaEventRecord(g_pipe.staged[k], g_pipe.copy));
+            KZG_CUDA(cudaStreamWaitEvent(g_pipe.heavy, g_pipe.staged[k], 0));
             d_sc = g_pipe.d_stage[k];
         }
+        // ... and so is its work area
+        if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(g_pipe.heavy, g_pipe.done[k], 0));
         const XYZZ* res = nullptr;
-        rc = msm_run(s, d_sc, m, ms_, &res, k, ts_, g_pipe.handoff[k]);
-        if (rc) break;
-        void* d_o = on_device ? (void*)((char*)out + i * osz) : (void*)((char*)g_pipe.d_out + i * 192);
+        int rc = msm_run(s, d_sc, m, g_pipe.heavy, &res, k, ts_, g_pipe.handoff[k]);
+        if (rc) return rc;
+        PipeDbg d{};
+        if (dbg) {
+            cudaEventCreate(&d.acc_done);
+            cudaEventRecord(d.acc_done, g_pipe.heavy);
+        }
+        void* d_o = out_dev ? (void*)((char*)out + i * osz) : (void*)((char*)g_pipe.d_out + i * 192);
         rc = msm_finish(res, d_o, mode, ts_);
-        if (rc) break;
-        if (!on_device)
+        if (rc) return rc;
+        if (!out_dev)
             KZG_CUDA(cudaMemcpyAsync((char*)g_pipe.h_out + i * 192, d_o, osz, cudaMemcpyDeviceToHost, ts_));
         KZG_CUDA(cudaEventRecord(g_pipe.done[k], ts_));
         g_pipe.used[k] = true;
-    }
-    // the batch is complete when both tails are; the device variant hands completion back to `after`
-    if (on_device && after && rc == KZGB_OK) {
-        for (int k = 0; k < 2 && (size_t)k < count; k++) KZG_CUDA(cudaStreamWaitEvent(after, g_pipe.done[k], 0));
-    } else {
-        for (int k = 0; k < 2; k++) {
-            cudaError_t e1 = cudaStreamSynchronize(g_pipe.main_s[k]);
-            cudaError_t e2 = cudaStreamSynchronize(g_pipe.tail_s[k]);
-            if (rc == KZGB_OK && e1 != cudaSuccess) rc = cuda_fail(e1, "sync(batch main)", __FILE__, __LINE__);
-            if (rc == KZGB_OK && e2 != cudaSuccess) rc = cuda_fail(e2, "sync(batch tail)", __FILE__, __LINE__);
+        if (dbg) {
+            cudaEventCreate(&d.done);
+            cudaEventRecord(d.done, ts_);
+            d.host_ms = now_ms() - h0;
+            g_dbg.push_back(d);
         }
     }
-    if (start_ev) cudaEventDestroy(start_ev);
-    if (rc == KZGB_OK && !on_device)
-        for (size_t i = 0; i < count; i++) memcpy((char*)out + i * osz, (char*)g_pipe.h_out + i * 192, osz);
+    // the batch is complete when both tails are; the device variant hands completion back to `after`
+    if (out_dev && after)
+        for (int k = 0; k < 2 && (size_t)k < count; k++) KZG_CUDA(cudaStreamWaitEvent(after, g_pipe.done[k], 0));
+    return KZGB_OK;
+}
+
+int msm_batch(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int where,
+              cudaStream_t after) {
+    const bool out_dev = (where & 2) != 0;
+    int rc = pipe_init();
+    if (rc) return rc;
+    if (after) {  // the heavy stream starts after the work already enqueued on the caller's stream
+        cudaEvent_t start_ev;
+        KZG_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+        KZG_CUDA(cudaEventRecord(start_ev, after));
+        KZG_CUDA(cudaStreamWaitEvent(g_pipe.heavy, start_ev, 0));
+        KZG_CUDA(cudaStreamWaitEvent(g_pipe.copy, start_ev, 0));
+        cudaEventDestroy(start_ev);
+    }
+    rc = msm_batch_run(s, scalars, ms, count, out, mode, where, after);
+    // errors, host output and host scalars (the caller may reuse its buffers on return): wait here
+    if (rc != KZGB_OK || !(out_dev && after) || !(where & 1) || pipe_debug()) rc = pipe_drain(rc);
+    if (pipe_debug() && g_dbg_start) {
+        fprintf(stderr, "[kzgb pipe] %zu items: host enqueue done at / accumulate done at / item done at (ms)\n", g_dbg.size());
+        for (size_t i = 0; i < g_dbg.size(); i++) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, g_dbg_start, g_dbg[i].acc_done);
+            cudaEventElapsedTime(&b, g_dbg_start, g_dbg[i].done);
+            fprintf(stderr, "[kzgb pipe] %2zu  %8.3f  %8.3f  %8.3f\n", i, g_dbg[i].host_ms, a, b);
+            cudaEventDestroy(g_dbg[i].acc_done);
+            cudaEventDestroy(g_dbg[i].done);
+        }
+        cudaEventDestroy(g_dbg_start);
+        g_dbg_start = nullptr;
+        g_dbg.clear();
+    }
+    if (rc == KZGB_OK && !out_dev)
+        for (size_t i = 0; i < count; i++) memcpy((char*)out + i * out_size(mode), (char*)g_pipe.h_out + i * 192, out_size(mode));
     return rc;
 }
 }  // namespace
@@ -267,7 +334,23 @@ KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* s, const void* const* d_scalars, co
     for (size_t i = 0; i < count; i++)
         if (ms[i] && !d_scalars[i]) { set_error("kzgb_msm_g1_batch_dev: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = pick_stream(stream);
-    return msm_batch(s, d_scalars, ms, count, d_out, out_mode, 1, st);
+    return msm_batch(s, d_scalars, ms, count, d_out, out_mode, 3, st);
+}
+
+// Host scalars in, device results out (the multi-GPU commit path from host buffers: the K partial sums stay on the
+// device for the all-gather).  Returns when the batch is complete (the host buffers may be reused).
+KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* s, const kzgb_fr* const* scalars, const size_t* ms, size_t count, void* d_out,
+                                   int out_mode, void* stream) {
+    KZG_REQUIRE_INIT();
+    KZG_LOCK();
+    if (!s || out_mode < 0 || out_mode > 2 || (count && (!scalars || !ms || !d_out))) {
+        set_error("kzgb_msm_g1_batch_h2d: bad argument");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    for (size_t i = 0; i < count; i++)
+        if (ms[i] && !scalars[i]) { set_error("kzgb_msm_g1_batch_h2d: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
+    cudaStream_t st = pick_stream(stream);
+    return msm_batch(s, (const void* const*)scalars, ms, count, d_out, out_mode, 2, st);
 }
 
 // Multi-GPU combine: `count` raw XYZZ partial sums (192 B each, device) -> one point.

@@ -53,6 +53,9 @@ class CudaOps:
         srs.msm_batch_dev([t.data_ptr() for t in scalars_list], [t.shape[0] for t in scalars_list], out_xyzz.data_ptr(), 2,
                           torch.cuda.current_stream().cuda_stream)
 
+    def msm_partial_many_host(self, srs: _ffi.SRS, host_scalars_list, out_xyzz: torch.Tensor) -> None:
+        srs.msm_batch_h2d(host_scalars_list, out_xyzz.data_ptr(), 2, torch.cuda.current_stream().cuda_stream)
+
     def msm_affine_many(self, srs: _ffi.SRS, scalars_list, out_affine: torch.Tensor) -> None:
         srs.msm_batch_dev([t.data_ptr() for t in scalars_list], [t.shape[0] for t in scalars_list], out_affine.data_ptr(), 0,
                           torch.cuda.current_stream().cuda_stream)
@@ -89,30 +92,52 @@ def sharded_msm(srs_shard, scalars_shard: torch.Tensor, ops=None, group=None) ->
     return out
 
 
-def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None) -> torch.Tensor:
+def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None, device=None) -> torch.Tensor:
     """`sharded_msm` for K polynomials at once: the K local MSMs run through the pipelined batch entry point, the K
-    partials travel in ONE all-gather (G x K x 192 bytes) and are combined on every rank -> int64[K, 12]."""
+    partials travel in ONE all-gather (G x K x 192 bytes) and are combined on every rank -> int64[K, 12].
+    `scalars_shards` are device tensors, or (with `device` given) host numpy arrays [m, 4] u64 whose copies are
+    pipelined with the MSMs."""
     ops = ops or CudaOps()
     k = len(scalars_shards)
-    dev = scalars_shards[0].device
+    from_host = device is not None
+    dev = device if from_host else scalars_shards[0].device
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     out = torch.zeros((k, 12), dtype=torch.int64, device=dev)
-    if world == 1 and hasattr(ops, "msm_affine_many"):
+    if world == 1 and hasattr(ops, "msm_affine_many") and not from_host:
         ops.msm_affine_many(srs_shard, scalars_shards, out)
         return out
+    dbg = os.environ.get("KZGB_PIPE_DEBUG") == "1" and dev.type == "cuda"
+    if dbg:
+        import time as _t
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        h = [_t.perf_counter()]
+        ev[0].record()
     partials = torch.zeros((k, 24), dtype=torch.int64, device=dev)
-    if hasattr(ops, "msm_partial_many"):
+    if from_host:
+        ops.msm_partial_many_host(srs_shard, scalars_shards, partials)
+    elif hasattr(ops, "msm_partial_many"):
         ops.msm_partial_many(srs_shard, scalars_shards, partials)
     else:
         for i, sc in enumerate(scalars_shards):
             ops.msm_partial(srs_shard, sc, partials[i])
+    if dbg:
+        ev[1].record(); h.append(_t.perf_counter())
     if world > 1:
         gathered = torch.empty((world, k, 24), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gathered.view(-1), partials.view(-1), group=group)
     else:
         gathered = partials.view(1, k, 24)
+    if dbg:
+        ev[2].record(); h.append(_t.perf_counter())
     if hasattr(ops, "g1_combine_many"):
         ops.g1_combine_many(gathered, world, k, out)
+        if dbg:
+            ev[3].record(); h.append(_t.perf_counter())
+            torch.cuda.synchronize()
+            import sys as _s
+            print("[kzgb many] k=%d gpu ms: batch %.3f allgather %.3f combine %.3f | host ms: %s" % (
+                k, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
+                [round((b - a) * 1e3, 3) for a, b in zip(h, h[1:])]), file=_s.stderr, flush=True)
     else:
         per_item = gathered.transpose(0, 1).contiguous()      # [k][world][24]
         for i in range(k):

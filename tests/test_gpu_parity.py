@@ -167,6 +167,15 @@ def test_msm_batch_pipelined_matches_single_calls(gpu, cpu):
     for i in range(K):
         e = cpu.g1_add(cpu.g1_add(J(singles[i]), J(singles[(i - 1) % K])), J(singles[(i - 2) % K]))
         assert (outs[i].cpu().numpy().view(np.uint64) == cpu.g1_to_affine(e)[0]).all()
+    # host scalars in, device results out (the multi-GPU commit path from host buffers)
+    xy2 = torch.zeros((K, 24), dtype=torch.int64, device="cuda")
+    srs.msm_batch_h2d(polys, xy2.data_ptr(), 2, st)
+    torch.cuda.synchronize()
+    assert torch.equal(xy2, xyzz)
+    from kzg_b200.distributed import sharded_msm_many as smm
+    o3 = smm(srs, [p for i, p in enumerate(polys) if i != 2], device=torch.device("cuda"))
+    torch.cuda.synchronize()
+    assert (o3.cpu().numpy().view(np.uint64) == np.delete(singles, 2, axis=0)).all()
     with pytest.raises(gpu.KZGBackendError):
         srs.msm_batch([np.zeros((n + 1, 4), dtype=np.uint64)])
     # host mirror
