@@ -104,12 +104,19 @@ struct NttScatter {
 };
 
 template <bool LAST, bool SCATTER>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
                                                                NttPassParams p, Fr minv, NttScatter sc) {
     extern __shared__ uint4 sm[];
     const uint32_t tid = threadIdx.x;
     const uint32_t R = 1u << p.log_r, T = 1u << p.log_t;
     const uint32_t E = R * T;
+    // Last pass only: consecutive lanes stage consecutive d of ONE row t, i.e. bit-reversed rows dr at the same
+    // column -- every lane of the warp on the same 16-byte bank group (32-way conflict).  XOR the column with the top
+    // three bits of the row: the 8 lanes of a quarter-warp then hit 8 different groups, and accesses along a row
+    // (the butterfly stages, the final read) stay conflict-free because the XOR permutes each aligned group of 8.
+    const uint32_t sw_shift = (LAST && p.log_r >= 3 && p.log_t >= 3) ? p.log_r - 3 : 0;
+    const uint32_t sw_mask = (LAST && p.log_r >= 3 && p.log_t >= 3) ? 7u : 0u;
+    auto SW = [&](uint32_t row, uint32_t col) { return (row << p.log_t) + (col ^ ((row >> sw_shift) & sw_mask)); };
     const uint64_t tile = blockIdx.x;
     // batched transforms: blockIdx.y selects one of gridDim.y independent length-2^log_n vectors
     in += (size_t)blockIdx.y * p.batch_stride;
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t t = e >> p.log_r, d = e & (R - 1);
             uint32_t dr = p.log_r ? (__brev(d) >> (32 - p.log_r)) : 0;
             uint64_t addr = (p.npass > 1) ? (((k10 + t) << log_s1) + (k2 << p.log_r) + d) : d;
-            sm_st(sm, (dr << p.log_t) + t, E, lds_fr(&in[addr]));
+            sm_st(sm, SW(dr, t), E, lds_fr(&in[addr]));
         }
     }
     __syncthreads();
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
     if (p.log_r & 1) {
         for (uint32_t b = tid; b < E / 2; b += NTT_THREADS) {
             uint32_t tl = b & (T - 1), bb = b >> p.log_t;
-            uint32_t i0 = ((bb << 1) << p.log_t) + tl;   // m = 1: pairs (2bb, 2bb+1), twiddle 1
-            uint32_t i1 = i0 + T;
+            uint32_t i0 = SW(bb << 1, tl);   // m = 1: pairs (2bb, 2bb+1), twiddle 1
+            uint32_t i1 = SW((bb << 1) + 1, tl);
             Fr u = sm_ld(sm, i0, E);
             Fr t = sm_ld(sm, i1, E);
             sm_st(sm, i0, E, u + t);
@@ -165,9 +172,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
             uint32_t tl = g & (T - 1), gg = g >> p.log_t;
             uint32_t j = gg & (m - 1);
             uint32_t k = (gg >> s) << (s + 2);
-            uint32_t i0 = ((k + j) << p.log_t) + tl;
-            uint32_t st = m << p.log_t;
-            Fr x0 = sm_ld(sm, i0, E), x1 = sm_ld(sm, i0 + st, E), x2 = sm_ld(sm, i0 + 2 * st, E), x3 = sm_ld(sm, i0 + 3 * st, E);
+            const uint32_t i0 = SW(k + j, tl), i1 = SW(k + j + m, tl), i2 = SW(k + j + 2 * m, tl), i3 = SW(k + j + 3 * m, tl);
+            Fr x0 = sm_ld(sm, i0, E), x1 = sm_ld(sm, i1, E), x2 = sm_ld(sm, i2, E), x3 = sm_ld(sm, i3, E);
             // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m)
             {
                 bool neg = false;
@@ -195,9 +201,9 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
                 x1 = neg2 ? e : d; x3 = neg2 ? d : e;
             }
             sm_st(sm, i0, E, x0);
-            sm_st(sm, i0 + st, E, x1);
-            sm_st(sm, i0 + 2 * st, E, x2);
-            sm_st(sm, i0 + 3 * st, E, x3);
+            sm_st(sm, i1, E, x1);
+            sm_st(sm, i2, E, x2);
+            sm_st(sm, i3, E, x3);
         }
         __syncthreads();
     }
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const Fr* in, Fr*
     } else {
         for (uint32_t e = tid; e < E; e += NTT_THREADS) {
             uint32_t kp = e >> p.log_t, t = e & (T - 1);
-            Fr v = sm_ld(sm, e, E);
+            Fr v = sm_ld(sm, SW(kp, t), E);
             if (p.apply_scale) v = v * minv;
             uint64_t idx = (p.npass > 1)
                                ? ((k10 + t) + (k2 << p.log_r1) + ((uint64_t)kp << (p.log_n - p.log_r)))
