@@ -106,12 +106,6 @@ def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None, device=Non
     if world == 1 and hasattr(ops, "msm_affine_many") and not from_host:
         ops.msm_affine_many(srs_shard, scalars_shards, out)
         return out
-    dbg = os.environ.get("KZGB_PIPE_DEBUG") == "1" and dev.type == "cuda"
-    if dbg:
-        import time as _t
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        h = [_t.perf_counter()]
-        ev[0].record()
     partials = torch.zeros((k, 24), dtype=torch.int64, device=dev)
     if from_host:
         ops.msm_partial_many_host(srs_shard, scalars_shards, partials)
@@ -120,24 +114,13 @@ def sharded_msm_many(srs_shard, scalars_shards, ops=None, group=None, device=Non
     else:
         for i, sc in enumerate(scalars_shards):
             ops.msm_partial(srs_shard, sc, partials[i])
-    if dbg:
-        ev[1].record(); h.append(_t.perf_counter())
     if world > 1:
         gathered = torch.empty((world, k, 24), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(gathered.view(-1), partials.view(-1), group=group)
     else:
         gathered = partials.view(1, k, 24)
-    if dbg:
-        ev[2].record(); h.append(_t.perf_counter())
     if hasattr(ops, "g1_combine_many"):
         ops.g1_combine_many(gathered, world, k, out)
-        if dbg:
-            ev[3].record(); h.append(_t.perf_counter())
-            torch.cuda.synchronize()
-            import sys as _s
-            print("[kzgb many] k=%d gpu ms: batch %.3f allgather %.3f combine %.3f | host ms: %s" % (
-                k, ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3]),
-                [round((b - a) * 1e3, 3) for a, b in zip(h, h[1:])]), file=_s.stderr, flush=True)
     else:
         per_item = gathered.transpose(0, 1).contiguous()      # [k][world][24]
         for i in range(k):
