@@ -120,6 +120,10 @@ KZGB_API int kzgb_msm_g1_batch(kzgb_srs* srs, const kzgb_fr* const* scalars, con
                                kzgb_p1_affine* out);
 KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* srs, const void* const* d_scalars, const size_t* ms, size_t count,
                                    void* d_out, int out_mode, void* stream);
+/* create_witness (coeff_form.rs:66-81) of one polynomial at m points in one pipelined call; p uploaded once.
+ * status[i] = 0 or 1 (PointNotOnPolynomial: out[i] unspecified).  Same bytes as m calls of kzgb_witness_coeff. */
+KZGB_API int kzgb_witness_coeff_many(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys,
+                                     size_t m, kzgb_p1_affine* out, int* status);
 /* host scalars in, device results out (multi-GPU commit from host buffers); returns when the batch is complete */
 KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* srs, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
                                    void* d_out, int out_mode, void* stream);

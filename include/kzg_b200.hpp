@@ -122,6 +122,20 @@ public:
         if (st == KZGB_POINT_NOT_ON_POLYNOMIAL) return {std::nullopt, KZGError::PointNotOnPolynomial};
         return {out, {}};
     }
+    // create_witness at every (xs[i], ys[i]) in one pipelined call (kzgb_witness_coeff_many); like collecting the
+    // per-point Results: the first point off the polynomial makes the whole call PointNotOnPolynomial
+    Result<std::vector<G1Affine>> create_witness_many(const Polynomial& p, const std::vector<Scalar>& xs,
+                                                      const std::vector<Scalar>& ys) const {
+        if (xs.size() != ys.size()) throw std::runtime_error("xs and ys differ in length");
+        std::vector<G1Affine> out(xs.size());
+        std::vector<int> status(xs.size() ? xs.size() : 1);
+        check(kzgb_witness_coeff_many(parameters_.handle(), p.slice_coeffs(), p.num_coeffs(), xs.data(), ys.data(), xs.size(),
+                                      out.data(), status.data()),
+              "kzgb_witness_coeff_many");
+        for (size_t i = 0; i < xs.size(); i++)
+            if (status[i] == KZGB_POINT_NOT_ON_POLYNOMIAL) return {std::nullopt, KZGError::PointNotOnPolynomial};
+        return {out, {}};
+    }
     Result<KZGBatchWitness> create_witness_batched(const Polynomial& p, const std::vector<Scalar>& xs,
                                                    const std::vector<Scalar>& ys) const {  // coeff_form.rs:83-111
         if (xs.size() != ys.size()) throw std::runtime_error("assertion failed: xs.len() == ys.len()");

@@ -305,6 +305,19 @@ def witness_coeff(srs: SRS, p, x, y):
     return st, out
 
 
+def witness_coeff_many(srs: SRS, p, xs, ys):
+    """create_witness of one polynomial at m points, pipelined: (status[m] int32, affine[m, 12])."""
+    p = u64(p, (-1, 4))
+    xs, ys = u64(xs, (-1, 4)), u64(ys, (-1, 4))
+    assert len(xs) == len(ys)
+    m = len(xs)
+    out = np.zeros((m, 12), dtype=np.uint64)
+    status = np.zeros(max(m, 1), dtype=np.int32)
+    check(lib().kzgb_witness_coeff_many(srs._h, ptr(p), C.c_size_t(len(p)), ptr(xs), ptr(ys), C.c_size_t(m), ptr(out),
+                                        status.ctypes.data_as(C.c_void_p)))
+    return status[:m], out
+
+
 def witness_coeff_dev(srs: SRS, d_p: int, n: int, d_xy: int, d_work: int, d_out: int, stream: int = 0) -> int:
     return check(lib().kzgb_witness_coeff_dev(srs._h, C.c_void_p(d_p), C.c_size_t(n), C.c_void_p(d_xy), C.c_void_p(d_work),
                                               C.c_void_p(d_out), C.c_void_p(stream)))

@@ -63,6 +63,19 @@ class KZGProver:
             raise PointNotOnPolynomial()
         return w
 
+    def create_witness_many(self, polynomial: Polynomial, xs, ys) -> np.ndarray:
+        """`create_witness` (coeff_form.rs:66-81) at every (xs[i], ys[i]) in one pipelined call -> [m, 12] G1Affine:
+        the polynomial is uploaded once and witness i's tail overlaps witness i+1's scan and accumulation.  Like
+        collecting the reference's Results: raises PointNotOnPolynomial (with `.index` = first offending point) if
+        any point is not on the polynomial.  An addition to the reference API for multi-opening workloads."""
+        st, w = _ffi.witness_coeff_many(self._parameters.srs, polynomial.slice_coeffs(), xs, ys)
+        bad = np.nonzero(st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL)[0]
+        if len(bad):
+            err = PointNotOnPolynomial()
+            err.index = int(bad[0])
+            raise err
+        return w
+
     def create_witness_batched(self, polynomial: Polynomial, xs, ys) -> KZGBatchWitness:
         """coeff_form.rs:83-111."""
         xs = _ffi.u64(xs, (-1, 4))

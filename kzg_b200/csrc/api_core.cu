@@ -3,6 +3,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
 
 namespace kzg {
 
@@ -229,6 +231,8 @@ int kzgb_shutdown(void) {
     std::lock_guard<std::recursive_mutex> g(c.mu);
     if (!c.initialised) return KZGB_OK;
     cudaStreamSynchronize(c.stream);
+    msm_pipe_shutdown();
+    ntt_free_twiddles();
     if (c.scratch) cudaFree(c.scratch);
     if (c.staging) cudaFree(c.staging);
     if (c.pinned) cudaFreeHost(c.pinned);

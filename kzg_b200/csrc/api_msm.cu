@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "ec.cuh"
 #include "msm.cuh"
+#include "scan.cuh"
 
 using namespace kzg;
 
@@ -175,6 +176,33 @@ int pipe_init() {
     return KZGB_OK;
 }
 
+}  // namespace
+
+extern "C++" {
+namespace kzg {
+// called by kzgb_shutdown: streams, events and buffers of the batch pipeline
+void msm_pipe_shutdown() {
+    if (!g_pipe.ready) return;
+    cudaStreamSynchronize(g_pipe.heavy);
+    cudaStreamSynchronize(g_pipe.copy);
+    for (int k = 0; k < 2; k++) {
+        cudaStreamSynchronize(g_pipe.tail_s[k]);
+        cudaStreamDestroy(g_pipe.tail_s[k]);
+        cudaEventDestroy(g_pipe.handoff[k]);
+        cudaEventDestroy(g_pipe.done[k]);
+        cudaEventDestroy(g_pipe.staged[k]);
+        if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
+    }
+    cudaStreamDestroy(g_pipe.heavy);
+    cudaStreamDestroy(g_pipe.copy);
+    if (g_pipe.d_out) cudaFree(g_pipe.d_out);
+    if (g_pipe.h_out) cudaFreeHost(g_pipe.h_out);
+    g_pipe = MsmPipe();
+}
+}  // namespace kzg
+}  // extern "C++"
+
+namespace {
 size_t out_size(int mode) { return mode == 0 ? sizeof(kzgb_p1_affine) : (mode == 1 ? sizeof(kzgb_p1) : 192); }
 
 int pipe_drain(int rc) {
@@ -351,6 +379,98 @@ KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* s, const kzgb_fr* const* scalars, c
         if (ms[i] && !scalars[i]) { set_error("kzgb_msm_g1_batch_h2d: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = pick_stream(stream);
     return msm_batch(s, (const void* const*)scalars, ms, count, d_out, out_mode, 2, st);
+}
+
+// create_witness (coeff_form.rs:66-81) of ONE polynomial at m points in one pipelined call (multi-opening workloads:
+// SURVEY 8 f2).  Item i = scan (p - y_i) / (X - x_i) on the heavy stream into the slot's quotient buffer, then the MSM of
+// the n-1 quotient coefficients; the tail of witness i overlaps the scan + accumulation of witness i+1, and p is
+// uploaded once.  status[i] = 0, or 1 (KZGB_POINT_NOT_ON_POLYNOMIAL: p(x_i) != y_i, coeff_form.rs:72-75; out[i] is
+// then unspecified, as the reference returns Err).  Same bytes as m calls of kzgb_witness_coeff.
+namespace {
+__global__ void batch_rem_flag_kernel(const Fr* rem, int* flag) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *flag = rem->is_zero() ? 0 : 1;
+}
+}  // namespace
+
+KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys, size_t m,
+                                     kzgb_p1_affine* out, int* status) {
+    KZG_REQUIRE_INIT();
+    KZG_LOCK();
+    use_stream(ctx().stream);
+    if (!s || !p || n == 0 || (m && (!xs || !ys || !out || !status))) {
+        set_error("kzgb_witness_coeff_many: bad argument");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    const size_t qn = n > 1 ? n - 1 : 1;   // psi has n-1 coefficients (n == 1: one zero coefficient)
+    if (qn > s->n) {
+        set_error("kzgb_witness_coeff_many: quotient has %zu coefficients but the SRS holds %zu points", qn, s->n);
+        return KZGB_ERR_INVALID_ARG;
+    }
+    if (m == 0) return KZGB_OK;
+    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
+    int rc = pipe_init();
+    if (rc) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    // staging arena: [p | (x_i, y_i) pairs | remainders | flags]; scan workspace in the scratch arena
+    const size_t pb = al(n * 32), xyb = al(m * 64), rb = al(m * 32), fb = al(m * sizeof(int));
+    char* buf = (char*)staging_reserve(pb + xyb + rb + fb);
+    if (!buf) return KZGB_ERR_CUDA;
+    char* ws = (char*)scratch_reserve(al(scan_workspace_bytes(n)));
+    if (!ws) return KZGB_ERR_CUDA;
+    Fr* d_p = (Fr*)buf;
+    Fr* d_xy = (Fr*)(buf + pb);
+    Fr* d_rem = (Fr*)(buf + pb + xyb);
+    int* d_flag = (int*)(buf + pb + xyb + rb);
+    if (g_pipe.out_bytes < m * 192) {
+        if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; }
+        KZG_CUDA(cudaMalloc(&g_pipe.d_out, m * 192));
+        KZG_CUDA(cudaMallocHost(&g_pipe.h_out, m * 192));
+        g_pipe.out_bytes = m * 192;
+    }
+    for (int k = 0; k < 2; k++) {
+        if (g_pipe.stage_bytes[k] < qn * 32) {
+            rc = pipe_drain(KZGB_OK);
+            if (rc) return rc;
+            if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
+            g_pipe.d_stage[k] = nullptr;
+            g_pipe.stage_bytes[k] = 0;
+            KZG_CUDA(cudaMalloc(&g_pipe.d_stage[k], qn * 32));
+            g_pipe.stage_bytes[k] = qn * 32;
+        }
+    }
+    cudaStream_t hs = g_pipe.heavy;
+    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, hs));
+    // interleave (x_i, y_i) on the device side: two strided copies
+    KZG_CUDA(cudaMemcpy2DAsync(d_xy, 64, xs, 32, 32, m, cudaMemcpyHostToDevice, hs));
+    KZG_CUDA(cudaMemcpy2DAsync(d_xy + 1, 64, ys, 32, 32, m, cudaMemcpyHostToDevice, hs));
+    for (size_t i = 0; i < m && rc == KZGB_OK; i++) {
+        const int k = (int)(i & 1);
+        cudaStream_t ts_ = g_pipe.tail_s[k];
+        if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(hs, g_pipe.done[k], 0));   // quotient buffer + work area free
+        Fr* d_q = (Fr*)g_pipe.d_stage[k];
+        rc = scan_divide_linear(d_p, n, d_xy + 2 * i, d_xy + 2 * i + 1, d_q, d_rem + i, ws, hs);
+        if (rc) break;
+        batch_rem_flag_kernel<<<1, 32, 0, hs>>>(d_rem + i, d_flag + i);
+        KZG_LAUNCHED();
+        if (n == 1) KZG_CUDA(cudaMemsetAsync(d_q, 0, 32, hs));
+        const XYZZ* res = nullptr;
+        rc = msm_run(s, d_q, qn, hs, &res, k, ts_, g_pipe.handoff[k]);
+        if (rc) break;
+        void* d_o = (char*)g_pipe.d_out + i * 192;
+        rc = msm_finish(res, d_o, 0, ts_);
+        if (rc) break;
+        KZG_CUDA(cudaMemcpyAsync((char*)g_pipe.h_out + i * 192, d_o, sizeof(kzgb_p1_affine), cudaMemcpyDeviceToHost, ts_));
+        KZG_CUDA(cudaEventRecord(g_pipe.done[k], ts_));
+        g_pipe.used[k] = true;
+    }
+    rc = pipe_drain(rc);
+    if (rc) return rc;
+    KZG_CUDA(cudaMemcpy(status, d_flag, m * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m; i++) {
+        status[i] = status[i] ? KZGB_POINT_NOT_ON_POLYNOMIAL : KZGB_OK;
+        memcpy(out + i, (char*)g_pipe.h_out + i * 192, sizeof(kzgb_p1_affine));
+    }
+    return KZGB_OK;
 }
 
 // Multi-GPU combine: `count` raw XYZZ partial sums (192 B each, device) -> one point.

@@ -38,5 +38,6 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
 int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream, uint32_t items = 1);
 // items > 1: partial of (rank g, item b) at index g*items + b; out[b] = sum over g
 int msm_combine(const void* d_partials_xyzz, uint32_t count, void* d_out_xyzz, cudaStream_t stream, uint32_t items = 1);
+void msm_pipe_shutdown();
 int jac_to_affine_dev(const void* d_jac, void* d_aff, size_t n, cudaStream_t stream);
 }  // namespace kzg

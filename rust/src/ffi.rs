@@ -27,6 +27,8 @@ extern "C" {
     pub fn kzgb_ntt_fr(inout: *mut Scalar, log_n: u32, inverse: c_int) -> c_int;
     pub fn kzgb_divide_linear(p: *const Scalar, n: usize, x: *const Scalar, y: *const Scalar, q_out: *mut Scalar, rem_out: *mut Scalar) -> c_int;
     pub fn kzgb_witness_coeff(srs: *mut kzgb_srs, p: *const Scalar, n: usize, x: *const Scalar, y: *const Scalar, out: *mut G1Affine) -> c_int;
+    pub fn kzgb_witness_coeff_many(srs: *mut kzgb_srs, p: *const Scalar, n: usize, xs: *const Scalar, ys: *const Scalar, m: usize,
+                                   out: *mut G1Affine, status: *mut c_int) -> c_int;
     pub fn kzgb_witness_batched(srs: *mut kzgb_srs, p: *const Scalar, n: usize, xs: *const Scalar, ys: *const Scalar, m: usize,
                                 r_out: *mut Scalar, r_len: *mut usize, w_out: *mut G1Affine) -> c_int;
     pub fn kzgb_div_by_omega_i(evals: *const Scalar, log_d: u32, i: usize, q_out: *mut Scalar) -> c_int;

@@ -46,6 +46,23 @@ pub fn create_witness(srs: &Srs, polynomial: &Polynomial, (x, y): (Scalar, Scala
     }
 }
 
+/// `create_witness` (coeff_form.rs:66-81) at every point of `points` in one pipelined call: an addition to the
+/// reference API (`KZGProver::create_witness_many`).  Equivalent to collecting the per-point `Result`s.
+pub fn create_witness_many(srs: &Srs, polynomial: &Polynomial, points: &[(Scalar, Scalar)]) -> Result<Vec<KZGWitness>, KZGError> {
+    let p = polynomial.slice_coeffs();
+    let xs: Vec<Scalar> = points.iter().map(|q| q.0).collect();
+    let ys: Vec<Scalar> = points.iter().map(|q| q.1).collect();
+    let mut out = vec![G1Affine::default(); points.len()];
+    let mut status = vec![0i32; points.len()];
+    ffi::check(unsafe {
+        ffi::kzgb_witness_coeff_many(srs.raw(), p.as_ptr(), p.len(), xs.as_ptr(), ys.as_ptr(), points.len(), out.as_mut_ptr(), status.as_mut_ptr())
+    }, "kzgb_witness_coeff_many");
+    if status.iter().any(|&s| s == ffi::KZGB_POINT_NOT_ON_POLYNOMIAL) {
+        return Err(KZGError::PointNotOnPolynomial); // coeff_form.rs:74
+    }
+    Ok(out)
+}
+
 /// `KZGProver::create_witness_batched` — coeff_form.rs:83-111.  Returns (r, w); the caller wraps them in
 /// `KZGBatchWitness { r, w }` (coeff_form.rs:105-108).
 pub fn create_witness_batched(srs: &Srs, polynomial: &Polynomial, xs: &[Scalar], ys: &[Scalar]) -> Result<(Polynomial, G1Affine), KZGError> {

@@ -45,3 +45,17 @@ for name in ("host sequential kzgb_msm_g1", "host pipelined kzgb_msm_g1_batch") 
     dt = (time.perf_counter() - t0) / K
     print("%-34s %.3f ms per commit  (%.3e points/s)" % (name, dt * 1e3, n / dt))
 print("host batch == host sequential:", bool((r == r2).all()))
+# multi-opening: witnesses of one polynomial at K points, pipelined vs one call at a time
+xs = cpu.fr_stream(7, K)
+p_host = harr[0]
+ys = np.vstack([cpu.poly_eval(p_host, xs[i]) for i in range(4)] + [np.zeros((K - 4, 4), dtype=np.uint64)])
+for name in ("witness sequential kzgb_witness_coeff", "witness pipelined kzgb_witness_coeff_many") * 2:
+    t0 = time.perf_counter()
+    if "sequential" in name:
+        rs = [_ffi.witness_coeff(srs, p_host, xs[i], ys[i]) for i in range(K)]
+    else:
+        st_many, w_many = _ffi.witness_coeff_many(srs, p_host, xs, ys)
+    dt = (time.perf_counter() - t0) / K
+    print("%-44s %.3f ms per witness" % (name, dt * 1e3))
+print("witness many == sequential:", all(int(st_many[i]) == rs[i][0] and (rs[i][0] != 0 or (w_many[i] == rs[i][1]).all()) for i in range(K)),
+      "statuses", [int(v) for v in st_many[:6]])

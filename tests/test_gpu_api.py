@@ -55,6 +55,31 @@ def test_commit_many_equals_commit_loop(params):
         prover.commit_many([polys[0], kzg.Polynomial.from_ints(list(range(1, 18)))])
 
 
+def test_create_witness_many_equals_loop(params):
+    """create_witness_many (kzgb_witness_coeff_many: one upload, pipelined scans + MSMs) == a loop of create_witness;
+    a point off the polynomial raises with its index; constant polynomials follow polynomial.rs:194-199."""
+    prover = kzg.KZGProver(params)
+    coeffs = O.fr_stream(42, 16)
+    poly = kzg.Polynomial.from_ints(coeffs)
+    xs = O.fr_stream(7, 7)
+    ys = [ev(coeffs, x) for x in xs]
+    many = prover.create_witness_many(poly, scalar.fr_vec(xs), scalar.fr_vec(ys))
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        assert (many[i] == prover.create_witness(poly, (scalar.fr(x), scalar.fr(y)))).all()
+        assert (many[i] == point((ev(coeffs, SECRET) - y) * pow(SECRET - x, -1, R))).all()
+    ys_bad = list(ys)
+    ys_bad[4] = (ys_bad[4] + 1) % R
+    with pytest.raises(kzg.PointNotOnPolynomial) as ei:
+        prover.create_witness_many(poly, scalar.fr_vec(xs), scalar.fr_vec(ys_bad))
+    assert ei.value.index == 4
+    const = kzg.Polynomial.from_ints([5])
+    w = prover.create_witness_many(const, scalar.fr_vec([3, 9]), scalar.fr_vec([5, 5]))   # psi = 0 -> identity
+    assert not w.any()
+    with pytest.raises(kzg.PointNotOnPolynomial):
+        prover.create_witness_many(const, scalar.fr_vec([3]), scalar.fr_vec([6]))
+    assert prover.create_witness_many(poly, scalar.fr_vec([]).reshape(0, 4), scalar.fr_vec([]).reshape(0, 4)).shape == (0, 12)
+
+
 def test_modify_single_coeff(params):
     """coeff_form.rs:295-311."""
     prover = kzg.KZGProver(params)
