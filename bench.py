@@ -382,6 +382,14 @@ def run_gpu(args):
             st = _ffi.witness_coeff_dev(srs, polys[0].data_ptr(), N_POINTS, xy.data_ptr(), work.data_ptr(), wout.data_ptr(), stream)
         extra["witness_2p20_ms"] = (time.perf_counter() - t0) / 5 * 1e3
         extra["witness_status"] = st
+        # multi-opening: create_witness at 8 points of one polynomial through the pipelined host-pointer call
+        xs8 = ocpu.fr_stream(7, 8)
+        ys8 = np.vstack([ocpu.poly_eval(host_views[0], xs8[i]) for i in range(8)])
+        _ffi.witness_coeff_many(srs, host_views[0], xs8[:2], ys8[:2])
+        t0 = time.perf_counter()
+        st8, _w8 = _ffi.witness_coeff_many(srs, host_views[0], xs8, ys8)
+        extra["witness_many_2p20_ms_per_point"] = (time.perf_counter() - t0) / 8 * 1e3
+        extra["witness_many_status"] = [int(v) for v in st8]
         # C4: create_witness_batched, 256 openings (interpolation + coset-NTT division + MSM), device resident
         m = 256
         xs_t = torch.empty((m, 4), dtype=torch.int64, device=dev)

@@ -62,6 +62,15 @@ class KZGProverEvalForm:
             raise IndexError("range end index out of range for slice")  # :117
         return self.lagrange_basis_g.msm(evals.coeffs)
 
+    def commit_many(self, evals_list) -> np.ndarray:
+        """`commit` (eval_form.rs:114-122) of several evaluation vectors in one pipelined call -> [count, 12]."""
+        evals_list = list(evals_list)
+        for evals in evals_list:
+            assert self.d == evals.d
+            if len(evals) > len(self.lagrange_basis_g):
+                raise IndexError("range end index out of range for slice")
+        return self.lagrange_basis_g.msm_batch([e.coeffs for e in evals_list])
+
     def create_witness(self, evals: EvaluationDomain, i: int) -> np.ndarray:
         # eval_form.rs:124-140 (infallible)
         if i >= len(evals.coeffs):

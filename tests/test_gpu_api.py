@@ -181,6 +181,9 @@ def test_eval_form_prover(golden):
     coeffs.ifft()
     mono = kzg.KZGProver(params).commit(coeffs.into_polynomial())     # verify_poly path, eval_form.rs:162-171
     assert (commitment == mono).all()
+    others = [kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(O.fr_stream(60 + k, d))) for k in range(3)]
+    many = prover.commit_many([evals] + others)                      # pipelined batch == commit in a loop
+    assert (many[0] == commitment).all() and all((many[k + 1] == prover.commit(e)).all() for k, e in enumerate(others))
     g = golden["eval"][0]
     assert scalar.g1_affine_compress(commitment).hex() == g["commit"]
     w = prover.create_witness(evals, 3)
