@@ -124,6 +124,9 @@ KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* srs, const void* const* d_scalars, 
  * status[i] = 0 or 1 (PointNotOnPolynomial: out[i] unspecified).  Same bytes as m calls of kzgb_witness_coeff. */
 KZGB_API int kzgb_witness_coeff_many(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys,
                                      size_t m, kzgb_p1_affine* out, int* status);
+/* eval-form create_witness (eval_form.rs:124-140) of one evaluation vector at m indices, pipelined; evals uploaded once */
+KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uint32_t log_d, const size_t* indices,
+                                    size_t m, kzgb_p1_affine* out);
 /* host scalars in, device results out (multi-GPU commit from host buffers); returns when the batch is complete */
 KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* srs, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
                                    void* d_out, int out_mode, void* stream);

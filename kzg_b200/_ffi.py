@@ -419,6 +419,17 @@ def ntt_batch_dev(d_inout: int, d_tmp: int, log_n: int, batch: int, inverse: boo
                                           C.c_int(int(inverse)), ptr(sc), C.c_void_p(stream)))
 
 
+def witness_eval_many(srs: SRS, evals, log_d: int, indices) -> np.ndarray:
+    """Eval-form create_witness at several indices of one evaluation vector, pipelined -> [m, 12]."""
+    evals = u64(evals, (-1, 4))
+    idx = [int(i) for i in indices]
+    m = len(idx)
+    arr = (C.c_size_t * max(m, 1))(*idx)
+    out = np.zeros((m, 12), dtype=np.uint64)
+    check(lib().kzgb_witness_eval_many(srs._h, ptr(evals), C.c_uint32(log_d), arr, C.c_size_t(m), ptr(out)))
+    return out
+
+
 def srs_lagrange_from_monomial(mono: SRS, log_d: int, window_bits: int = 0) -> SRS:
     """Secret-free Lagrange-basis SRS (eval_form.rs:254-280) as a group inverse NTT of the monomial SRS."""
     h = C.c_void_p()

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "ec.cuh"
+#include "evalform.cuh"
 #include "msm.cuh"
 #include "scan.cuh"
 
@@ -381,6 +382,45 @@ KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* s, const kzgb_fr* const* scalars, c
     return msm_batch(s, (const void* const*)scalars, ms, count, d_out, out_mode, 2, st);
 }
 
+// ---- shared pieces of the "many witnesses" entry points (host results; scalars produced on the heavy stream) ----
+namespace {
+int pipe_reserve_results(size_t count) {
+    if (g_pipe.out_bytes >= count * 192) return KZGB_OK;
+    if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; g_pipe.out_bytes = 0; }
+    KZG_CUDA(cudaMalloc(&g_pipe.d_out, count * 192));
+    KZG_CUDA(cudaMallocHost(&g_pipe.h_out, count * 192));
+    g_pipe.out_bytes = count * 192;
+    return KZGB_OK;
+}
+int pipe_reserve_stage(size_t bytes) {   // both slots; drains the pipeline when it has to grow
+    for (int k = 0; k < 2; k++) {
+        if (g_pipe.stage_bytes[k] >= bytes) continue;
+        int rc = pipe_drain(KZGB_OK);
+        if (rc) return rc;
+        if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
+        g_pipe.d_stage[k] = nullptr;
+        g_pipe.stage_bytes[k] = 0;
+        KZG_CUDA(cudaMalloc(&g_pipe.d_stage[k], bytes));
+        g_pipe.stage_bytes[k] = bytes;
+    }
+    return KZGB_OK;
+}
+// MSM of the m scalars in the slot's stage buffer -> affine result i (device + pinned mirror); releases the slot
+int pipe_msm_item(kzgb_srs* s, int k, size_t m, size_t i) {
+    cudaStream_t ts_ = g_pipe.tail_s[k];
+    const XYZZ* res = nullptr;
+    int rc = msm_run(s, g_pipe.d_stage[k], m, g_pipe.heavy, &res, k, ts_, g_pipe.handoff[k]);
+    if (rc) return rc;
+    void* d_o = (char*)g_pipe.d_out + i * 192;
+    rc = msm_finish(res, d_o, 0, ts_);
+    if (rc) return rc;
+    KZG_CUDA(cudaMemcpyAsync((char*)g_pipe.h_out + i * 192, d_o, sizeof(kzgb_p1_affine), cudaMemcpyDeviceToHost, ts_));
+    KZG_CUDA(cudaEventRecord(g_pipe.done[k], ts_));
+    g_pipe.used[k] = true;
+    return KZGB_OK;
+}
+}  // namespace
+
 // create_witness (coeff_form.rs:66-81) of ONE polynomial at m points in one pipelined call (multi-opening workloads:
 // SURVEY 8 f2).  Item i = scan (p - y_i) / (X - x_i) on the heavy stream into the slot's quotient buffer, then the MSM of
 // the n-1 quotient coefficients; the tail of witness i overlaps the scan + accumulation of witness i+1, and p is
@@ -421,23 +461,7 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
     Fr* d_xy = (Fr*)(buf + pb);
     Fr* d_rem = (Fr*)(buf + pb + xyb);
     int* d_flag = (int*)(buf + pb + xyb + rb);
-    if (g_pipe.out_bytes < m * 192) {
-        if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; }
-        KZG_CUDA(cudaMalloc(&g_pipe.d_out, m * 192));
-        KZG_CUDA(cudaMallocHost(&g_pipe.h_out, m * 192));
-        g_pipe.out_bytes = m * 192;
-    }
-    for (int k = 0; k < 2; k++) {
-        if (g_pipe.stage_bytes[k] < qn * 32) {
-            rc = pipe_drain(KZGB_OK);
-            if (rc) return rc;
-            if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
-            g_pipe.d_stage[k] = nullptr;
-            g_pipe.stage_bytes[k] = 0;
-            KZG_CUDA(cudaMalloc(&g_pipe.d_stage[k], qn * 32));
-            g_pipe.stage_bytes[k] = qn * 32;
-        }
-    }
+    if ((rc = pipe_reserve_results(m)) || (rc = pipe_reserve_stage(qn * 32))) return rc;
     cudaStream_t hs = g_pipe.heavy;
     KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, hs));
     // interleave (x_i, y_i) on the device side: two strided copies
@@ -445,7 +469,6 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
     KZG_CUDA(cudaMemcpy2DAsync(d_xy + 1, 64, ys, 32, 32, m, cudaMemcpyHostToDevice, hs));
     for (size_t i = 0; i < m && rc == KZGB_OK; i++) {
         const int k = (int)(i & 1);
-        cudaStream_t ts_ = g_pipe.tail_s[k];
         if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(hs, g_pipe.done[k], 0));   // quotient buffer + work area free
         Fr* d_q = (Fr*)g_pipe.d_stage[k];
         rc = scan_divide_linear(d_p, n, d_xy + 2 * i, d_xy + 2 * i + 1, d_q, d_rem + i, ws, hs);
@@ -453,15 +476,7 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
         batch_rem_flag_kernel<<<1, 32, 0, hs>>>(d_rem + i, d_flag + i);
         KZG_LAUNCHED();
         if (n == 1) KZG_CUDA(cudaMemsetAsync(d_q, 0, 32, hs));
-        const XYZZ* res = nullptr;
-        rc = msm_run(s, d_q, qn, hs, &res, k, ts_, g_pipe.handoff[k]);
-        if (rc) break;
-        void* d_o = (char*)g_pipe.d_out + i * 192;
-        rc = msm_finish(res, d_o, 0, ts_);
-        if (rc) break;
-        KZG_CUDA(cudaMemcpyAsync((char*)g_pipe.h_out + i * 192, d_o, sizeof(kzgb_p1_affine), cudaMemcpyDeviceToHost, ts_));
-        KZG_CUDA(cudaEventRecord(g_pipe.done[k], ts_));
-        g_pipe.used[k] = true;
+        rc = pipe_msm_item(s, k, qn, i);
     }
     rc = pipe_drain(rc);
     if (rc) return rc;
@@ -470,6 +485,48 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
         status[i] = status[i] ? KZGB_POINT_NOT_ON_POLYNOMIAL : KZGB_OK;
         memcpy(out + i, (char*)g_pipe.h_out + i * 192, sizeof(kzgb_p1_affine));
     }
+    return KZGB_OK;
+}
+
+// KZGProverEvalForm::create_witness (eval_form.rs:124-140) of one evaluation vector at m indices in one pipelined
+// call: evals uploaded once; item j = div_by_omega_i (eval_form.rs:58-84) at indices[j] into the slot's quotient
+// buffer, then the MSM over the Lagrange-basis SRS.  Same bytes as m calls of kzgb_witness_eval (which is infallible).
+KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uint32_t log_d, const size_t* indices,
+                                    size_t m, kzgb_p1_affine* out) {
+    KZG_REQUIRE_INIT();
+    KZG_LOCK();
+    use_stream(ctx().stream);
+    if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
+    const size_t d = (size_t)1 << log_d;
+    if (!lagrange_srs || !evals || (m && (!indices || !out)) || d > lagrange_srs->n) {
+        set_error("kzgb_witness_eval_many: bad argument");
+        return KZGB_ERR_INVALID_ARG;
+    }
+    for (size_t j = 0; j < m; j++)
+        if (indices[j] >= d) { set_error("kzgb_witness_eval_many: index %zu out of bounds", indices[j]); return KZGB_ERR_INVALID_ARG; }
+    if (m == 0) return KZGB_OK;
+    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
+    int rc = pipe_init();
+    if (rc) return rc;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char* d_evals = (char*)staging_reserve(al(d * 32));
+    if (!d_evals) return KZGB_ERR_CUDA;
+    char* ws = (char*)scratch_reserve(al(div_by_omega_workspace_bytes(log_d)) + 256);
+    if (!ws) return KZGB_ERR_CUDA;
+    if ((rc = pipe_reserve_results(m)) || (rc = pipe_reserve_stage(d * 32))) return rc;
+    cudaStream_t hs = g_pipe.heavy;
+    KZG_CUDA(cudaMemcpyAsync(d_evals, evals, d * 32, cudaMemcpyHostToDevice, hs));
+    for (size_t j = 0; j < m && rc == KZGB_OK; j++) {
+        const int k = (int)(j & 1);
+        if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(hs, g_pipe.done[k], 0));
+        if (log_d == 0) KZG_CUDA(cudaMemsetAsync(g_pipe.d_stage[k], 0, 32, hs));
+        else rc = div_by_omega_run((const Fr*)d_evals, log_d, (uint32_t)indices[j], (Fr*)g_pipe.d_stage[k], ws, hs);
+        if (rc) break;
+        rc = pipe_msm_item(lagrange_srs, k, d, j);
+    }
+    rc = pipe_drain(rc);
+    if (rc) return rc;
+    for (size_t j = 0; j < m; j++) memcpy(out + j, (char*)g_pipe.h_out + j * 192, sizeof(kzgb_p1_affine));
     return KZGB_OK;
 }
 

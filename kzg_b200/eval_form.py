@@ -77,6 +77,15 @@ class KZGProverEvalForm:
             raise IndexError("index out of bounds")  # evals.coeffs[i], :125
         return _ffi.witness_eval(self.lagrange_basis_g, evals.coeffs, evals.exp, i)
 
+    def create_witness_many(self, evals: EvaluationDomain, indices) -> np.ndarray:
+        """`create_witness` (eval_form.rs:124-140) at every index of `indices` in one pipelined call -> [m, 12]:
+        the evaluation vector is uploaded once and witness j's tail overlaps witness j+1's division and accumulation."""
+        indices = [int(i) for i in indices]
+        for i in indices:
+            if i >= len(evals.coeffs):
+                raise IndexError("index out of bounds")
+        return _ffi.witness_eval_many(self.lagrange_basis_g, evals.coeffs, evals.exp, indices)
+
     def create_witness_all(self) -> np.ndarray:
         # eval_form.rs:142-146: identity * 0
         return G1_IDENTITY_AFFINE.copy()

@@ -184,6 +184,11 @@ def test_eval_form_prover(golden):
     others = [kzg.EvaluationDomain.from_coeffs(scalar.fr_vec(O.fr_stream(60 + k, d))) for k in range(3)]
     many = prover.commit_many([evals] + others)                      # pipelined batch == commit in a loop
     assert (many[0] == commitment).all() and all((many[k + 1] == prover.commit(e)).all() for k, e in enumerate(others))
+    idx = [0, 5, 15, 5, 9]
+    wm = prover.create_witness_many(evals, idx)                        # pipelined multi-opening == loop
+    assert all((wm[j] == prover.create_witness(evals, i)).all() for j, i in enumerate(idx))
+    with pytest.raises(IndexError):
+        prover.create_witness_many(evals, [3, 16])
     g = golden["eval"][0]
     assert scalar.g1_affine_compress(commitment).hex() == g["commit"]
     w = prover.create_witness(evals, 3)
