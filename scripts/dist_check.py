@@ -23,6 +23,21 @@ if rank == 0:
     coeffs = cpu.fr_stream(42, total)
     expect = cpu.g1_to_affine(cpu.g1_mul(cpu.g1_generator(), cpu.poly_eval(coeffs, s)))[0]
     print("sharded MSM parity (%d ranks, %d points):" % (world, total), bool((out.cpu().numpy().view(np.uint64) == expect).all()), flush=True)
+# ---- K polynomials at once (pipelined batch + one all-gather + batched combine), device and host scalars ----
+scs = []
+for b in range(3):
+    t = torch.empty((per, 4), dtype=torch.int64, device=dev)
+    _ffi.fr_stream_dev(t.data_ptr(), 42 + b, per, start=rank * per, stream=torch.cuda.current_stream().cuda_stream)
+    scs.append(t)
+many = kd.sharded_msm_many(srs, scs)
+many_h = kd.sharded_msm_many(srs, [t.cpu().numpy().view(np.uint64) for t in scs], device=dev)
+torch.cuda.synchronize()
+if rank == 0:
+    oks = []
+    for b in range(3):
+        cf = cpu.g1_to_affine(cpu.g1_mul(cpu.g1_generator(), cpu.poly_eval(cpu.fr_stream(42 + b, total), s)))[0]
+        oks.append(bool((many[b].cpu().numpy().view(np.uint64) == cf).all()) and bool((many_h[b].cpu().numpy().view(np.uint64) == cf).all()))
+    print("sharded_msm_many parity, device and host scalars (%d ranks, 3 polynomials):" % world, oks, flush=True)
 # ---- four-step NTT 2^LOG ----
 n = 1 << LOG
 l1, l2, lc = kd.four_step_shape(LOG, world)
