@@ -55,6 +55,8 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
+            if os.environ.get("KZGB_BENCH_NO_POLLER") == "1":   # diagnostic: is the poller perturbing host-synchronous loops?
+                raise RuntimeError("poller disabled")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                           "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
@@ -385,7 +387,7 @@ def run_gpu(args):
         # multi-opening: create_witness at 8 points of one polynomial through the pipelined host-pointer call
         xs8 = ocpu.fr_stream(7, 8)
         ys8 = np.vstack([ocpu.poly_eval(host_views[0], xs8[i]) for i in range(8)])
-        _ffi.witness_coeff_many(srs, host_views[0], xs8[:2], ys8[:2])
+        _ffi.witness_coeff_many(srs, host_views[0], xs8, ys8)   # warm-up at the timed size
         t0 = time.perf_counter()
         st8, _w8 = _ffi.witness_coeff_many(srs, host_views[0], xs8, ys8)
         extra["witness_many_2p20_ms_per_point"] = (time.perf_counter() - t0) / 8 * 1e3

@@ -204,6 +204,7 @@ void msm_pipe_shutdown() {
 }  // extern "C++"
 
 namespace {
+int pipe_reserve_results(size_t count);   // defined with the many-witness helpers below
 size_t out_size(int mode) { return mode == 0 ? sizeof(kzgb_p1_affine) : (mode == 1 ? sizeof(kzgb_p1) : 192); }
 
 int pipe_drain(int rc) {
@@ -236,11 +237,9 @@ int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, siz
         cudaEventCreate(&g_dbg_start);
         cudaEventRecord(g_dbg_start, g_pipe.heavy);
     }
-    if (!out_dev && count && g_pipe.out_bytes < count * 192) {
-        if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; }
-        KZG_CUDA(cudaMalloc(&g_pipe.d_out, count * 192));
-        KZG_CUDA(cudaMallocHost(&g_pipe.h_out, count * 192));
-        g_pipe.out_bytes = count * 192;
+    if (!out_dev && count) {
+        int rc = pipe_reserve_results(count);
+        if (rc) return rc;
     }
     for (size_t i = 0; i < count; i++) {
         const int k = (int)(i & 1);
@@ -386,6 +385,7 @@ KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* s, const kzgb_fr* const* scalars, c
 namespace {
 int pipe_reserve_results(size_t count) {
     if (g_pipe.out_bytes >= count * 192) return KZGB_OK;
+    if (count < 256) count = 256;   // pinned allocations are slow (up to 0.1 s): never regrow for a handful of results
     if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; g_pipe.out_bytes = 0; }
     KZG_CUDA(cudaMalloc(&g_pipe.d_out, count * 192));
     KZG_CUDA(cudaMallocHost(&g_pipe.h_out, count * 192));
