@@ -10,6 +10,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 _ffi.init(local)
 LOG = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+LOG_N1 = int(sys.argv[2]) if len(sys.argv) > 2 else None   # four-step split (default: four_step_shape's choice)
 # ---- sharded MSM over world * 2^18 points ----
 per = 1 << 18
 total = per * world
@@ -40,7 +41,7 @@ if rank == 0:
     print("sharded_msm_many parity, device and host scalars (%d ranks, 3 polynomials):" % world, oks, flush=True)
 # ---- four-step NTT 2^LOG ----
 n = 1 << LOG
-l1, l2, lc = kd.four_step_shape(LOG, world)
+l1, l2, lc = kd.four_step_shape(LOG, world, LOG_N1)
 n1, c = 1 << l1, 1 << lc
 # generate this rank's slab directly: slab[i1][cc] = a[i1*N2 + rank*C + cc] ; build from the full stream on host (rank-local slices)
 full = cpu.fr_stream(5, n) if rank == 0 else None
@@ -49,12 +50,12 @@ for i1 in range(n1):   # device-side generation row by row (stream positions are
     _ffi.fr_stream_dev(slab[i1].data_ptr(), 5, c, start=i1 * (1 << l2) + rank * c, stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 work = slab.clone()
-rows = kd.ntt_four_step(work, LOG, False)
+rows = kd.ntt_four_step(work, LOG, False, log_n1=LOG_N1)
 torch.cuda.synchronize()
 gathered = [torch.empty_like(rows) for _ in range(world)]
 dist.all_gather(gathered, rows) if world > 1 else gathered.__setitem__(0, rows)
 if rank == 0:
-    got = kd.four_step_gather([g.cpu().numpy().view(np.uint64) for g in gathered], LOG, world)
+    got = kd.four_step_gather([g.cpu().numpy().view(np.uint64) for g in gathered], LOG, world, LOG_N1)
     ref_t = torch.from_numpy(full.view(np.int64)).to(dev)
     tmp = torch.empty_like(ref_t)
     _ffi.ntt_dev(ref_t.data_ptr(), LOG, False, torch.cuda.current_stream().cuda_stream)
@@ -63,7 +64,7 @@ if rank == 0:
     del ref_t, tmp
 # timing (max over ranks)
 for _ in range(2):
-    work.copy_(slab); kd.ntt_four_step(work, LOG, False)
+    work.copy_(slab); kd.ntt_four_step(work, LOG, False, log_n1=LOG_N1)
 if world > 1: dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -73,7 +74,7 @@ for _ in range(K):
     work.copy_(slab)
     torch.cuda.synchronize()
     if world > 1: dist.barrier()
-    e0.record(); kd.ntt_four_step(work, LOG, False); e1.record()
+    e0.record(); kd.ntt_four_step(work, LOG, False, log_n1=LOG_N1); e1.record()
     torch.cuda.synchronize()
     tot += e0.elapsed_time(e1)
 t = torch.tensor([tot / K], device=dev, dtype=torch.float64)
@@ -81,12 +82,12 @@ if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print("four-step NTT 2^%d on %d GPU(s): %.3f ms (max over ranks)" % (LOG, world, t.item()), flush=True)
 # ---- fused exchange: column pass stores into the peers' row matrices (CUDA IPC over NVLink) ----
-plan = kd.FourStepPeerPlan(LOG)
+plan = kd.FourStepPeerPlan(LOG, log_n1=LOG_N1)
 ok = True
 for it in range(4):           # alternates the two row matrices; inverse on odd calls
     inv = bool(it & 1)
     work.copy_(slab)
-    ref = kd.ntt_four_step(work, LOG, inv)
+    ref = kd.ntt_four_step(work, LOG, inv, log_n1=LOG_N1)
     fused = kd.ntt_four_step_fused(slab, plan, inv)
     ok = ok and bool(torch.equal(ref, fused))
 torch.cuda.synchronize()
