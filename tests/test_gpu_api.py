@@ -302,3 +302,16 @@ def test_verify_poly_and_wire_formats(gpu, params):
     assert (gpu.fr_from_bytes_le(b) == scalar.fr_vec(vals)).all()
     with pytest.raises(gpu.KZGBackendError):
         gpu.fr_from_bytes_le(R.to_bytes(32, "little"))                    # r itself is not canonical
+
+
+def test_cpp_host_mirror_demo_runs():
+    """The header-only C++ mirror (include/kzg_b200.hpp) end to end in its own process: commit, create_witness,
+    commit_many, create_witness_many, rejection of a point off the polynomial, kzgb_shutdown."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "host_mirror_demo")
+    if not os.path.exists(exe):
+        pytest.skip("build/host_mirror_demo not built (make)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "commit_many ok=1 create_witness_many ok=1 bad rejected=1" in r.stdout
