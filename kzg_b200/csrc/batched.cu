@@ -41,16 +41,43 @@ KZG_DI void b_st(Fr* p, const Fr& v) {
 }
 
 // ---- K11: interpolation ------------------------------------------------------
-// Z(X) = prod (X - x_i): one block, coefficients ping-pong between two global buffers.
+// These kernels work on m <= 4096 values: a handful of warps each, so their cost is the LENGTH OF THE DEPENDENT CHAIN
+// per thread (a dependent Fr product costs ~0.3-0.6 us), not arithmetic.  Every output is therefore computed by a
+// group of IL = 8 adjacent lanes that split the chain and combine with shuffles (field sums and products are exact,
+// so the grouping does not change a single bit of the result).
+constexpr uint32_t IL = 8;
+KZG_DI Fr fr_shfl_xor(const Fr& v, int mask) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], mask);
+    return r;
+}
+
+// Z(X) = prod (X - x_i): one block; two roots per step (new[k] = old[k-2] - (a+b) old[k-1] + ab old[k]), coefficients
+// ping-pong between two buffers in shared memory (global memory for m too large to fit).
 __global__ void __launch_bounds__(1024) interp_product_kernel(const Fr* __restrict__ xs, uint32_t m, Fr* buf0, Fr* buf1,
-                                                              Fr* __restrict__ z_out) {
-    Fr* cur = buf0;
-    Fr* nxt = buf1;
+                                                              Fr* __restrict__ z_out, int use_smem) {
+    extern __shared__ uint4 interp_sm[];
+    Fr* cur = use_smem ? reinterpret_cast<Fr*>(interp_sm) : buf0;
+    Fr* nxt = use_smem ? reinterpret_cast<Fr*>(interp_sm) + (m + 1) : buf1;
     for (uint32_t k = threadIdx.x; k <= m; k += blockDim.x) cur[k] = (k == 0) ? Fr::one() : Fr::zero();
     __syncthreads();
-    for (uint32_t i = 0; i < m; i++) {
+    uint32_t i = 0;
+    for (; i + 1 < m; i += 2) {
+        const Fr a = xs[i], b = xs[i + 1];
+        const Fr sum = a + b, prod = a * b;
+        // degree i -> i+2 (old[j] = 0 outside 0..i)
+        for (uint32_t k = threadIdx.x; k <= i + 2; k += blockDim.x) {
+            Fr v = (k >= 2) ? cur[k - 2] : Fr::zero();
+            if (k >= 1 && k - 1 <= i) v = v - sum * cur[k - 1];
+            if (k <= i) v = v + prod * cur[k];
+            nxt[k] = v;
+        }
+        __syncthreads();
+        Fr* t = cur; cur = nxt; nxt = t;
+    }
+    if (i < m) {  // odd m: one more root.  degree i -> i+1 :  new[k] = old[k-1] - x_i * old[k]
         const Fr xi = xs[i];
-        // degree i -> i+1 :  new[k] = old[k-1] - x_i * old[k]
         for (uint32_t k = threadIdx.x; k <= i + 1; k += blockDim.x) {
             Fr v = (k >= 1) ? cur[k - 1] : Fr::zero();
             if (k <= i) v = v - xi * cur[k];
@@ -63,30 +90,40 @@ __global__ void __launch_bounds__(1024) interp_product_kernel(const Fr* __restri
 }
 
 // c_i = y_i / prod_{j != i} (x_i - x_j);   flag |= 2 when two x coincide (the reference panics:
-// `c.invert().unwrap()`, polynomial.rs:260)
-__global__ void interp_weights_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ ys, uint32_t m,
-                                      Fr* __restrict__ c, int* __restrict__ flag) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const Fr xi = xs[i];
+// `c.invert().unwrap()`, polynomial.rs:260).  IL lanes per i: lane r takes the factors j = r (mod IL).
+__global__ void __launch_bounds__(128) interp_weights_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ ys, uint32_t m,
+                                                             Fr* __restrict__ c, int* __restrict__ flag) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = gid / IL, r = gid % IL;
+    const bool active = i < m;     // inactive lanes still take part in the shuffles
     Fr d = Fr::one();
-    for (uint32_t j = 0; j < m; j++) {
-        if (j != i) d = d * (xi - xs[j]);
+    if (active) {
+        const Fr xi = xs[i];
+        for (uint32_t j = r; j < m; j += IL)
+            if (j != i) d = d * (xi - xs[j]);
     }
-    if (d.is_zero()) atomicOr(flag, 2);
-    c[i] = ys[i] * d.inv();
+    for (int o = IL / 2; o > 0; o >>= 1) d = d * fr_shfl_xor(d, o);
+    if (active && r == 0) {
+        if (d.is_zero()) atomicOr(flag, 2);
+        c[i] = ys[i] * d.inv();
+    }
 }
 
-// T[e][i] = c_i * x_i^e
-__global__ void interp_powers_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ c, uint32_t m,
-                                     Fr* __restrict__ T) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// T[e][i] = c_i * x_i^e.  IL lanes per i: lane r walks e = r (mod IL) with ratio x_i^IL.
+__global__ void __launch_bounds__(128) interp_powers_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ c, uint32_t m,
+                                                            Fr* __restrict__ T) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = gid / IL, r = gid % IL;
     if (i >= m) return;
     const Fr xi = xs[i];
+    Fr step = xi;
+#pragma unroll
+    for (uint32_t t = 1; t < IL; t <<= 1) step = step.sqr();   // x^IL (IL is a power of two)
     Fr v = c[i];
-    for (uint32_t e = 0; e < m; e++) {
+    for (uint32_t t = 0; t < r; t++) v = v * xi;               // c * x^r
+    for (uint32_t e = r; e < m; e += IL) {
         b_st(&T[(size_t)e * m + i], v);
-        v = v * xi;
+        v = v * step;
     }
 }
 
@@ -105,13 +142,17 @@ __global__ void __launch_bounds__(128) interp_powersum_kernel(const Fr* __restri
     if (threadIdx.x == 0) P[e] = sh[0];
 }
 
-// r_k = sum_{l=k+1}^{m} Z_l * P_{l-k-1}
-__global__ void interp_conv_kernel(const Fr* __restrict__ Z, const Fr* __restrict__ P, uint32_t m, Fr* __restrict__ r) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
+// r_k = sum_{l=k+1}^{m} Z_l * P_{l-k-1}.  IL lanes per k: lane r takes l = k+1+r (mod IL).
+__global__ void __launch_bounds__(128) interp_conv_kernel(const Fr* __restrict__ Z, const Fr* __restrict__ P, uint32_t m,
+                                                          Fr* __restrict__ r_out) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = gid / IL, r = gid % IL;
+    const bool active = k < m;
     Fr acc = Fr::zero();
-    for (uint32_t l = k + 1; l <= m; l++) acc = acc + Z[l] * P[l - k - 1];
-    r[k] = acc;
+    if (active)
+        for (uint32_t l = k + 1 + r; l <= m; l += IL) acc = acc + Z[l] * P[l - k - 1];
+    for (int o = IL / 2; o > 0; o >>= 1) acc = acc + fr_shfl_xor(acc, o);
+    if (active && r == 0) r_out[k] = acc;
 }
 
 // one-point case: r = X + (y - x)  (polynomial.rs:244-247 -- reproduced, not "fixed")
@@ -259,15 +300,22 @@ int interpolate_run(const Fr* d_xs, const Fr* d_ys, size_t m, Fr* d_r, Fr* d_Z, 
     Fr* P = c + (m + 1);
     Fr* T = P + (m + 1);
     uint32_t mm = (uint32_t)m;
-    interp_product_kernel<<<1, 1024, 0, stream>>>(d_xs, mm, buf0, buf1, d_Z);
+    const size_t prod_smem = 2 * (m + 1) * sizeof(Fr);
+    const int use_smem = prod_smem <= 96 * 1024;
+    static bool prod_attr_set = false;
+    if (use_smem && !prod_attr_set) {
+        KZG_CUDA(cudaFuncSetAttribute(interp_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        prod_attr_set = true;
+    }
+    interp_product_kernel<<<1, 1024, use_smem ? prod_smem : 0, stream>>>(d_xs, mm, buf0, buf1, d_Z, use_smem);
     KZG_LAUNCHED();
-    interp_weights_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_xs, d_ys, mm, c, d_flag);
+    interp_weights_kernel<<<div_up(m * IL, 128), 128, 0, stream>>>(d_xs, d_ys, mm, c, d_flag);
     KZG_LAUNCHED();
-    interp_powers_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_xs, c, mm, T);
+    interp_powers_kernel<<<div_up(m * IL, 128), 128, 0, stream>>>(d_xs, c, mm, T);
     KZG_LAUNCHED();
     interp_powersum_kernel<<<mm, 128, 0, stream>>>(T, mm, P);
     KZG_LAUNCHED();
-    interp_conv_kernel<<<div_up(m, 64), 64, 0, stream>>>(d_Z, P, mm, d_r);
+    interp_conv_kernel<<<div_up(m * IL, 128), 128, 0, stream>>>(d_Z, P, mm, d_r);
     KZG_LAUNCHED();
     return KZGB_OK;
 }
