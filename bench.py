@@ -49,7 +49,7 @@ class ClockSampler:
 
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index, period_ms=100):
+    def __init__(self, index, period_ms=50):
         self.rows = []          # (monotonic time, [fields])
         self.t0 = self.t1 = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -350,7 +350,7 @@ def run_gpu(args):
         extra["msm_whole_frac_of_imad_peak"] = IMAD_PER_POINT_MSM * N_POINTS / (ms_step * 1e-3) / imad_peak if world == 1 else None
 
     # ---- secondary headline: Fr NTT 2^22 (single GPU) and the C2 witness ----
-    if world == 1:
+    def secondary():
         peaks = measured_peaks()
         hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
         nbuf = torch.empty((1 << NTT_LOG, 4), dtype=torch.int64, device=dev)
@@ -416,6 +416,13 @@ def run_gpu(args):
         # roofline of the same dominant kernel seen from HBM (for completeness; it is not the binding roof)
         if acc_ms and peaks:
             extra["accumulate_hbm_view"] = {"algorithmic_GBps": (N_POINTS * 13 * 104) / (acc_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak}
+
+
+    if world == 1:
+        try:   # secondary measurements never take the headline line down
+            secondary()
+        except Exception as ex:   # noqa: BLE001
+            extra["secondary_error"] = repr(ex)[:300]
 
     cpu_baseline = None
     if world == 1:
