@@ -214,6 +214,49 @@ def test_four_step_layout_roundtrip():
     assert (kd.four_step_gather(blocks, log_n, world, log_n1=3) == X).all()
 
 
+@pytest.mark.parametrize("log_n,world,log_n1", [(6, 1, 3), (6, 2, 2), (7, 4, 3), (8, 8, 4), (8, 4, 6), (9, 2, None)])
+def test_four_step_layouts_any_world_single_process(log_n, world, log_n1):
+    """The index algebra of both four-step variants for several world sizes and splits, every rank emulated in this
+    process with the oracle-backed stand-ins: all-to-all variant (columns -> row blocks -> unpack -> rows) and fused
+    variant (columns_scatter straight into the owners' row matrices) must both equal the plain transform."""
+    from oracle import cpu
+    cpu.build()
+    vec = cpu.fr_stream(5, 1 << log_n)
+    l1, l2, lc = kd.four_step_shape(log_n, world, log_n1)
+    n1, c = 1 << l1, 1 << lc
+    nrows = n1 // world
+    ops = OraclePeerOps(cpu)
+    for inverse in (False, True):
+        expect = cpu.fft(vec, log_n, inverse, 1)
+        scale = np.array(O.fr_to_mont_limbs(pow(1 << log_n, -1, R)), dtype=np.uint64) if inverse else None
+        slabs = [_from_np(s).clone() for s in kd.four_step_scatter(vec, log_n, world, log_n1)]
+        # all-to-all variant
+        done = [t.clone() for t in slabs]
+        for g in range(world):
+            ops.columns(done[g], log_n, l1, lc, g * c, inverse)
+        blocks = []
+        for h in range(world):
+            recv = torch.stack([done[g].view(world, nrows, c, 4)[h] for g in range(world)]).contiguous()
+            rows = ops.unpack(recv, world, nrows, c)
+            ops.rows(rows, l2, inverse, scale)
+            blocks.append(_to_np(rows))
+        assert (kd.four_step_gather(blocks, log_n, world, log_n1) == expect).all()
+        # fused variant: every rank stores into every owner's matrix
+        allocs = [ops.peer_alloc(nrows * (1 << l2) * 32) for _ in range(world)]
+        peers = [p for p, _ in allocs]
+        for g in range(world):
+            ops.columns_scatter(slabs[g], peers, g, log_n, l1, lc, g * c, inverse)
+        blocks = []
+        for h in range(world):
+            rows = ops.wrap(peers[h], nrows * (1 << l2) * 32).view(nrows, 1 << l2, 4)
+            ops.rows(rows, l2, inverse, scale)
+            blocks.append(_to_np(rows).copy())
+        del rows
+        assert (kd.four_step_gather(blocks, log_n, world, log_n1) == expect).all()
+        for p in peers:
+            ops.peer_free(p)
+
+
 def test_world_size_2_gloo_msm_and_ntt():
     world = 2
     port = _free_port()
