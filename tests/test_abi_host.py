@@ -62,6 +62,27 @@ def test_compute_fails_loudly_without_gpu():
     assert len(lib.kzgb_last_error_message()) > 0
     with pytest.raises(_ffi.KZGBackendError):
         _ffi.check(st)
+    # every compute entry point of the hot path refuses to run without an initialised B200 (no CPU fallback):
+    # all of them must return a negative status before touching their (here: null) arguments
+    null = ctypes.c_void_p(0)
+    z = ctypes.c_size_t(0)
+    calls = {
+        "kzgb_msm_g1": (null, null, z, null),
+        "kzgb_msm_g1_batch": (null, null, null, z, null),
+        "kzgb_msm_g1_batch_dev": (null, null, null, z, null, ctypes.c_int(0), null),
+        "kzgb_msm_g1_batch_h2d": (null, null, null, z, null, ctypes.c_int(0), null),
+        "kzgb_witness_coeff": (null, null, z, null, null, null),
+        "kzgb_witness_coeff_many": (null, null, z, null, null, z, null, null),
+        "kzgb_witness_eval_many": (null, null, ctypes.c_uint32(0), null, z, null),
+        "kzgb_witness_batched": (null, null, z, null, null, z, null, null, null),
+        "kzgb_divide_linear": (null, z, null, null, null, null),
+        "kzgb_ntt4_columns_scatter_dev": (null, null, ctypes.c_uint32(1), ctypes.c_uint32(0), ctypes.c_uint32(4), ctypes.c_uint32(2),
+                                          ctypes.c_uint32(2), ctypes.c_uint32(0), ctypes.c_int(0), null),
+        "kzgb_peer_alloc": (z, null, null),
+        "kzgb_g1_combine_batch_dev": (null, ctypes.c_uint32(1), ctypes.c_uint32(1), null, ctypes.c_int(0), null),
+    }
+    for name, args in calls.items():
+        assert getattr(lib, name)(*args) < 0, name
 
 
 def test_scalar_encodings_roundtrip_and_match_oracle():
