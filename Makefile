@@ -1,15 +1,19 @@
 # Builds kzg_b200/libkzg_b200.so (sm_100a only) and the CPU oracle.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v
+# A/B builds of the library for experiments: make BUILD=build_x LIB=kzg_b200/libkzg_b200_x.so EXTRA="-DKZG_..." lib
+# (select at run time with KZGB_LIB=<path>); the default build takes no EXTRA flags.
+EXTRA ?=
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v $(EXTRA)
 SRC_DIR := kzg_b200/csrc
-BUILD := build
+BUILD ?= build
 SRCS := $(wildcard $(SRC_DIR)/*.cu)
 OBJS := $(patsubst $(SRC_DIR)/%.cu,$(BUILD)/%.o,$(SRCS))
 HDRS := $(wildcard $(SRC_DIR)/*.cuh) include/kzg_b200.h
-LIB := kzg_b200/libkzg_b200.so
+LIB ?= kzg_b200/libkzg_b200.so
 
 all: $(LIB) oracle $(BUILD)/host_mirror_demo
+lib: $(LIB)
 
 # compile check of the header-only C++ host mirror (runs only on a GPU box)
 $(BUILD)/host_mirror_demo: tests/cpp/host_mirror_demo.cpp include/kzg_b200.hpp include/kzg_b200.h $(LIB)
@@ -29,4 +33,4 @@ clean:
 	rm -rf $(BUILD) $(LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all lib oracle clean

@@ -15,6 +15,47 @@ Context& ctx() {
     return c;
 }
 
+static thread_local Lane* t_lane = nullptr;
+static thread_local int t_depth = 0;
+
+Lane& lane() {
+    // outside an ApiScope (library-internal misuse) fall back to lane 0 rather than dereferencing null
+    return t_lane ? *t_lane : ctx().lanes[0];
+}
+
+ApiScope::ApiScope() {
+    Context& c = ctx();
+    if (t_depth++ > 0) return;   // nested entry point: the outer scope holds the lane and the device
+    outer = true;
+    if (cudaGetDevice(&prev_device) != cudaSuccess) prev_device = -1;
+    if (prev_device != c.device) err = cudaSetDevice(c.device);
+    std::unique_lock<std::mutex> g(c.mu);
+    for (;;) {
+        for (int i = 0; i < KZG_MAX_LANES; i++) {
+            if (!c.lanes[i].busy) {
+                c.lanes[i].busy = true;
+                t_lane = &c.lanes[i];
+                break;
+            }
+        }
+        if (t_lane) break;
+        c.cv.wait(g);
+    }
+    if (!t_lane->stream && err == cudaSuccess) err = cudaStreamCreateWithFlags(&t_lane->stream, cudaStreamNonBlocking);
+}
+
+ApiScope::~ApiScope() {
+    if (--t_depth > 0 || !outer) return;
+    Context& c = ctx();
+    {
+        std::lock_guard<std::mutex> g(c.mu);
+        if (t_lane) t_lane->busy = false;
+        t_lane = nullptr;
+    }
+    c.cv.notify_one();
+    if (prev_device >= 0 && prev_device != c.device) cudaSetDevice(prev_device);
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -28,23 +69,29 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 cudaStream_t use_stream(cudaStream_t s) {
-    Context& c = ctx();
-    if (c.have_last && c.last_stream != s) cudaStreamSynchronize(c.last_stream);
-    c.last_stream = s;
-    c.have_last = true;
+    Lane& l = lane();
+    if (l.have_last && l.last_stream != s) cudaStreamSynchronize(l.last_stream);
+    l.last_stream = s;
+    l.have_last = true;
     return s;
 }
 
+// Arena growth frees the old block: everything that may still be reading it (the lane's last stream) is drained first.
+static void lane_drain(Lane& l) {
+    if (l.have_last) cudaStreamSynchronize(l.last_stream);
+    if (l.stream) cudaStreamSynchronize(l.stream);
+}
+
 void* scratch_reserve(size_t bytes) {
-    Context& c = ctx();
+    Lane& c = lane();
     if (bytes <= c.scratch_bytes) return c.scratch;
     if (c.scratch) {
-        cudaDeviceSynchronize();
+        lane_drain(c);
         cudaFree(c.scratch);
         c.scratch = nullptr;
         c.scratch_bytes = 0;
     }
-    // never smaller than 4 MiB: growing the arena synchronises the device and goes through cudaFree/cudaMalloc
+    // never smaller than 4 MiB: growing the arena synchronises and goes through cudaFree/cudaMalloc
     // (measured: up to 0.5 s with several processes on one box), so tiny requests must not trigger it repeatedly
     size_t want = bytes + (bytes >> 2);
     if (want < ((size_t)4 << 20)) want = (size_t)4 << 20;
@@ -58,10 +105,10 @@ void* scratch_reserve(size_t bytes) {
 }
 
 void* staging_reserve(size_t bytes) {
-    Context& c = ctx();
+    Lane& c = lane();
     if (bytes <= c.staging_bytes) return c.staging;
     if (c.staging) {
-        cudaDeviceSynchronize();
+        lane_drain(c);
         cudaFree(c.staging);
         c.staging = nullptr;
         c.staging_bytes = 0;
@@ -76,10 +123,10 @@ void* staging_reserve(size_t bytes) {
 }
 
 void* pinned_reserve(size_t bytes) {
-    Context& c = ctx();
+    Lane& c = lane();
     if (bytes <= c.pinned_bytes) return c.pinned;
     if (c.pinned) {
-        cudaStreamSynchronize(c.stream);
+        lane_drain(c);
         cudaFreeHost(c.pinned);
         c.pinned = nullptr;
         c.pinned_bytes = 0;
@@ -94,11 +141,13 @@ void* pinned_reserve(size_t bytes) {
 }
 
 // ---- stage timer ----
+// (diagnostics; one mutex of their own: they are shared by all lanes)
 struct StageRec { int stage; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
 static bool g_prof = false;
 static std::vector<StageRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
-static cudaEvent_t g_open[ST_COUNT];
+static thread_local cudaEvent_t t_open[ST_COUNT];
 
 static cudaEvent_t get_event() {
     if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
@@ -108,16 +157,18 @@ static cudaEvent_t get_event() {
 }
 void stage_begin(int stage, cudaStream_t stream) {
     if (!g_prof) return;
+    std::lock_guard<std::mutex> g(g_prof_mu);
     cudaEvent_t e = get_event();
     cudaEventRecord(e, stream);
-    g_open[stage] = e;
+    t_open[stage] = e;
 }
 void stage_end(int stage, cudaStream_t stream) {
-    if (!g_prof || !g_open[stage]) return;
+    if (!g_prof || !t_open[stage]) return;
+    std::lock_guard<std::mutex> g(g_prof_mu);
     cudaEvent_t e = get_event();
     cudaEventRecord(e, stream);
-    g_recs.push_back(StageRec{stage, g_open[stage], e});
-    g_open[stage] = nullptr;
+    g_recs.push_back(StageRec{stage, t_open[stage], e});
+    t_open[stage] = nullptr;
 }
 
 // ---- per-launch trace ----
@@ -126,20 +177,34 @@ static bool g_trace = false;
 static std::vector<TraceRec> g_trace_recs;
 void trace_mark(const char* file, int line) {
     if (!g_trace) return;
-    Context& c = ctx();
+    std::lock_guard<std::mutex> g(g_prof_mu);
+    Lane& l = lane();
     cudaEvent_t e = get_event();
-    cudaEventRecord(e, c.have_last ? c.last_stream : c.stream);
+    cudaEventRecord(e, l.have_last ? l.last_stream : l.stream);
     g_trace_recs.push_back(TraceRec{file, line, e});
+}
+
+// ---- live SRS handles (kzgb_shutdown releases their device memory; see msm.cuh) ----
+static std::mutex g_srs_mu;
+static std::vector<kzgb_srs*> g_live_srs;
+void srs_register(kzgb_srs* s) {
+    std::lock_guard<std::mutex> g(g_srs_mu);
+    g_live_srs.push_back(s);
+}
+void srs_unregister(kzgb_srs* s) {
+    std::lock_guard<std::mutex> g(g_srs_mu);
+    for (size_t i = 0; i < g_live_srs.size(); i++)
+        if (g_live_srs[i] == s) { g_live_srs[i] = g_live_srs.back(); g_live_srs.pop_back(); break; }
 }
 
 }  // namespace kzg
 
 using namespace kzg;
 
-// on = 1: start tracing (a first mark is recorded on the library stream); on = 0: stop
+// on = 1: start tracing; on = 0: stop
 extern "C" KZGB_API int kzgb_trace_enable(int on) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    std::lock_guard<std::mutex> g(g_prof_mu);
     g_trace = on != 0;
     return KZGB_OK;
 }
@@ -147,8 +212,9 @@ extern "C" KZGB_API int kzgb_trace_enable(int on) {
 // the previous mark (0 for the first); returns the number of records (negative on error) and clears the trace.
 extern "C" KZGB_API int kzgb_trace_read(int* lines, float* ms, int cap) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     KZG_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> g(g_prof_mu);
     int n = 0;
     for (size_t i = 0; i < g_trace_recs.size(); i++) {
         if (n < cap) {
@@ -165,7 +231,7 @@ extern "C" KZGB_API int kzgb_trace_read(int* lines, float* ms, int cap) {
 }
 
 extern "C" KZGB_API int kzgb_profile_enable(int on) {
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    std::lock_guard<std::mutex> g(g_prof_mu);
     g_prof = on != 0;
     return KZGB_OK;
 }
@@ -173,8 +239,9 @@ extern "C" KZGB_API int kzgb_profile_enable(int on) {
 // (arrays of at least kzgb_profile_stage_count() entries, zeroed by the caller) and clears the records.
 extern "C" KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     KZG_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> g(g_prof_mu);
     for (auto& r : g_recs) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
@@ -198,7 +265,7 @@ extern "C" {
 
 int kzgb_init(int device) {
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
+    std::lock_guard<std::mutex> g(c.mu);
     if (c.initialised) {
         if (c.device == device) return KZGB_OK;
         set_error("kzgb_init: already initialised on device %d", c.device);
@@ -210,7 +277,6 @@ int kzgb_init(int device) {
         set_error("kzgb_init: device %d out of range (%d visible)", device, count);
         return KZGB_ERR_INVALID_ARG;
     }
-    KZG_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     KZG_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -218,8 +284,9 @@ int kzgb_init(int device) {
                   prop.minor);
         return KZGB_ERR_INVALID_ARG;
     }
+    // The device is selected per call and per thread by ApiScope (CUDA's current device is thread-local), and the
+    // caller's own current device is left as it was.
     c.sm_count = prop.multiProcessorCount;
-    KZG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     c.device = device;
     c.initialised = true;
     c.launches = 0;
@@ -228,29 +295,41 @@ int kzgb_init(int device) {
 
 int kzgb_shutdown(void) {
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
     if (!c.initialised) return KZGB_OK;
-    cudaStreamSynchronize(c.stream);
-    msm_pipe_shutdown();
-    ntt_free_twiddles();
-    if (c.scratch) cudaFree(c.scratch);
-    if (c.staging) cudaFree(c.staging);
-    if (c.pinned) cudaFreeHost(c.pinned);
-    c.staging = nullptr;
-    c.staging_bytes = 0;
-    cudaStreamDestroy(c.stream);
-    c.scratch = nullptr;
-    c.scratch_bytes = 0;
-    c.pinned = nullptr;
-    c.pinned_bytes = 0;
-    c.stream = nullptr;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    comm_shutdown();
+    {   // live SRS handles: release their device memory now; kzgb_srs_destroy then only frees the host struct
+        std::lock_guard<std::mutex> g(g_srs_mu);
+        for (kzgb_srs* s : g_live_srs) srs_release_device(s);
+        g_live_srs.clear();
+    }
+    {
+        std::lock_guard<std::mutex> g(c.cache_mu);
+        for (int i = 0; i < 33; i++) {
+            if (c.ntt_tw[i]) cudaFree(c.ntt_tw[i]);
+            c.ntt_tw[i] = nullptr;
+        }
+        c.ntt_attr_set = false;   // cudaFuncSetAttribute is per device: a re-init elsewhere must set it again
+    }
+    std::lock_guard<std::mutex> g(c.mu);
+    for (Lane& l : c.lanes) {
+        if (l.scratch) cudaFree(l.scratch);
+        if (l.staging) cudaFree(l.staging);
+        if (l.pinned) cudaFreeHost(l.pinned);
+        if (l.stream) cudaStreamDestroy(l.stream);
+        l = Lane();
+    }
     c.initialised = false;
-    c.have_last = false;
+    if (prev >= 0 && prev != c.device) cudaSetDevice(prev);
+    c.device = -1;
     return KZGB_OK;
 }
 
 const char* kzgb_last_error_message(void) { return g_err; }
 
-uint64_t kzgb_launch_count(void) { return ctx().launches; }
+uint64_t kzgb_launch_count(void) { return ctx().launches.load(); }
 
 }  // extern "C"

@@ -4,37 +4,66 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
 
 #include "../../include/kzg_b200.h"
 
 namespace kzg {
 
+// One in-flight API call.  A lane owns a stream (host-pointer entry points run on it) and the three arenas a call may
+// use; a thread holds exactly one lane for the duration of a public call (nested calls share it), so calls from
+// different host threads overlap on the device instead of queueing behind one process-wide mutex.  Lane 0 is always
+// tried first: a single-threaded caller only ever touches one set of arenas.
+struct Lane {
+    cudaStream_t stream = nullptr;       // library-owned stream for host-pointer entry points
+    cudaStream_t last_stream = nullptr;  // stream of the previous call that used this lane's arenas (see use_stream)
+    bool have_last = false;
+    bool busy = false;
+    void* pinned = nullptr;   // pinned staging (host-pointer entry points)
+    size_t pinned_bytes = 0;
+    void* scratch = nullptr;  // device scratch arena (grown on demand, reused across calls)
+    size_t scratch_bytes = 0;
+    void* staging = nullptr;  // device copies of host-pointer inputs (outer level; scratch is the inner level)
+    size_t staging_bytes = 0;
+};
+constexpr int KZG_MAX_LANES = 4;
+
+
 struct Context {
     bool initialised = false;
     int device = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;  // library-owned stream for host-pointer entry points
-    cudaStream_t last_stream = nullptr;  // stream of the previous API call (arenas are shared: see use_stream)
-    bool have_last = false;
-    std::recursive_mutex mu;
-    uint64_t launches = 0;
-    // pinned staging (host-pointer entry points)
-    void* pinned = nullptr;
-    size_t pinned_bytes = 0;
-    // device scratch arena (grown on demand, reused across calls)
-    void* scratch = nullptr;
-    size_t scratch_bytes = 0;
-    // device staging arena: device copies of host-pointer inputs (outer level; scratch is the inner level)
-    void* staging = nullptr;
-    size_t staging_bytes = 0;
+    std::mutex mu;                 // guards lanes[].busy and init/shutdown
+    std::condition_variable cv;    // a lane was released
+    Lane lanes[KZG_MAX_LANES];
+    std::atomic<uint64_t> launches{0};
+    // per-device caches shared by every lane (built once, then read-only): NTT twiddle tables and kernel attributes
+    std::mutex cache_mu;
+    void* ntt_tw[33] = {nullptr};
+    bool ntt_attr_set = false;
 };
 
 Context& ctx();
+Lane& lane();   // the calling thread's lane (valid inside an ApiScope)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
-// Every entry point runs its work on ONE stream.  The scratch/staging arenas and per-SRS work areas are shared
-// between calls, so when consecutive calls use different streams the earlier stream is drained first.
+
+// RAII guard of every public entry point: selects the library's device on the calling thread (entry points may be
+// called from any host thread -- the reference's provers are Send + Sync, coeff_form.rs:37-41 -- and CUDA's current
+// device is per thread), acquires a lane, and on exit restores the caller's device.  Nested entry points reuse the
+// outer scope's lane.
+struct ApiScope {
+    int prev_device = -1;
+    bool outer = false;
+    cudaError_t err = cudaSuccess;
+    ApiScope();
+    ~ApiScope();
+};
+
+// Every entry point runs its work on ONE stream.  A lane's arenas (and an SRS handle's work areas, see msm.cuh) are
+// reused between calls, so when consecutive users run on different streams the earlier stream is drained first.
 cudaStream_t use_stream(cudaStream_t s);
 void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
 void* staging_reserve(size_t bytes);   // device staging for host-pointer entry points
@@ -53,6 +82,12 @@ void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr
             return KZGB_ERR_NOT_INITIALISED;                                        \
         }                                                                           \
     } while (0)
+
+// first statement (after KZG_REQUIRE_INIT) of every public entry point that touches the device
+#define KZG_ENTER()                                                                 \
+    ::kzg::ApiScope _api_scope;                                                     \
+    if (_api_scope.err != cudaSuccess)                                              \
+        return ::kzg::cuda_fail(_api_scope.err, "cudaSetDevice(library device)", __FILE__, __LINE__)
 
 // count + check a kernel launch
 #define KZG_LAUNCHED()                                                              \

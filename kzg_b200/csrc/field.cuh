@@ -15,13 +15,48 @@
 // (= 2*N^2 wide mads): 288 for Fq, 128 for Fr.
 #pragma once
 #include <cstdint>
+#if defined(KZG_HOST_EMU) && !defined(__CUDACC__)
+// plain g++ build of the host model (tests/cpp/field_host_model.cpp): CUDA keywords vanish, device intrinsics that
+// the checked routines never reach are declared (not defined) so that the template bodies still parse
+#define __host__
+#define __device__
+#define __constant__
+#define __forceinline__ inline
+#define __noinline__
+double __hiloint2double(int, int);
+int __double2loint(double);
+int __double2hiint(double);
+double __fma_rn(double, double, double);
+unsigned __funnelshift_l(unsigned, unsigned, unsigned);
+unsigned __funnelshift_r(unsigned, unsigned, unsigned);
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace kzg {
 
 // --------------------------------------------------------------------------
 // PTX carry-chain primitives
 // --------------------------------------------------------------------------
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+// Host emulation of the carry-chain primitives (tests/cpp/field_host_model.cu): the SAME limb-level routines are
+// compiled for the host with the PTX condition-code register modelled by one thread-local bit, so that new
+// multiplication schedules are checked bit-exact against a big-integer model without a GPU.  Never part of the library.
+#define KZG_DI inline
+namespace emu { static thread_local uint32_t cf = 0; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + emu::cf; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a + b + emu::cf); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; emu::cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - emu::cf; emu::cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a - b - emu::cf); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_lo(a, b) + c; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_lo(a, b) + c + emu::cf; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)mul_hi(a, b) + c + emu::cf; emu::cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((uint64_t)mul_hi(a, b) + c + emu::cf); }
+#else
 #define KZG_DI __device__ __forceinline__
 
 KZG_DI uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -36,6 +71,15 @@ KZG_DI uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm 
 KZG_DI uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 KZG_DI uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 KZG_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#endif
+
+KZG_DI uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {   // (hi:lo << sh) >> 32, 0 < sh < 32
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+    return (hi << sh) | (lo >> (32 - sh));
+#else
+    return __funnelshift_l(lo, hi, sh);
+#endif
+}
 
 // --------------------------------------------------------------------------
 // Field parameter packs (all values verified against the big-int oracle)
@@ -84,7 +128,13 @@ struct FrParams {
         return t[i];
     }
     static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
-    __device__ __forceinline__ static uint32_t inv32() { return FR_INV32_C[0]; }
+    KZG_DI static uint32_t inv32() {
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+        return INV;
+#else
+        return FR_INV32_C[0];
+#endif
+    }
     __host__ __device__ static constexpr uint32_t one(int i) {
         constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
                                         0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
@@ -189,6 +239,9 @@ struct Fe {
 #ifdef KZG_ROLLED_FQ_MUL
         if constexpr (N == 12) return mul_rolled(a, b);
 #endif
+#ifdef KZG_FR_KARATSUBA
+        if constexpr (N == 8) return mul_kara(a, b);
+#endif
         return mul_inline(a, b);
     }
     // One b-limb step of the interleaved product: X is the accumulator that currently plays "even", Y "odd".
@@ -233,7 +286,12 @@ struct Fe {
         r.final_sub();
         return r;
     }
-    __device__ __noinline__ static Fe mul_outlined(Fe a, Fe b) { return mul_inline(a, b); }
+    __device__ __noinline__ static Fe mul_outlined(Fe a, Fe b) {
+#ifdef KZG_FQ_KARATSUBA
+        if constexpr (N == 12) return mul_kara(a, b);
+#endif
+        return mul_inline(a, b);
+    }
     KZG_DI static Fe mul_inline(const Fe& a, const Fe& b) {
         uint32_t E[N], O[N];
         // ---- i = 0: plain products, no accumulation ----
@@ -438,7 +496,7 @@ struct Fe {
         for (int k = 2; k < M - 1; k++) T[k] = addc_cc(A[k], B[k - 1]);
         T[M - 1] = addc(A[M - 1], B[M - 2]);
 #pragma unroll
-        for (int k = M - 1; k > 0; k--) T[k] = __funnelshift_l(T[k - 1], T[k], 1);
+        for (int k = M - 1; k > 0; k--) T[k] = funnel_l(T[k - 1], T[k], 1);
         T[0] <<= 1;
         T[0] = mad_lo_cc(a.l[0], a.l[0], T[0]);
         T[1] = madc_hi_cc(a.l[0], a.l[0], T[1]);
@@ -448,8 +506,176 @@ struct Fe {
             if (i < N - 1) T[2 * i + 1] = madc_hi_cc(a.l[i], a.l[i], T[2 * i + 1]);
             else T[2 * i + 1] = madc_hi(a.l[i], a.l[i], T[2 * i + 1]);
         }
-        return mont_reduce_wide(T);
+        return redc_wide(T);
     }
+
+    // ------------------------------------------------------------------------------------------------------
+    // Product / reduction split ("wide" schedule).  IMAD.WIDE issues at 32 lanes/clk/SM while IADD3/LOP3 issue at
+    // 128: three of every four issue slots of a scheduler that is saturating the FMA-heavy pipe are free.  One level
+    // of (subtractive) Karatsuba trades a quarter of the N*N partial products of a*b for additions on the ALU pipe:
+    //   a*b = z0 + (z0 + z2 + (a0-a1)(b1-b0)) 2^(16N) + z2 2^(32N),  z0 = a0*b0, z2 = a1*b1      (3 (N/2)^2 products)
+    // followed by a word-serial Montgomery reduction of the 2N-limb product: 108 + 144 wide multiply-adds per Fq
+    // product instead of 288 (Fr: 48 + 64 instead of 128).  Keeping product and reduction apart also allows LAZY
+    // reduction: a*b - c*d costs two wide products and ONE reduction (mul_sub_mul).
+    // Bit-exactness of every routine below is checked on the host against a big-integer model
+    // (tests/cpp/field_host_model.cu, run by tests/test_field_host_model.py) and on the device (test op 9..11).
+    // ------------------------------------------------------------------------------------------------------
+    // H x H limb schoolbook product -> 2H limbs.  Partial products a_j*b_i with i+j even accumulate in A (register
+    // pair (k, k+1), k = i+j), those with i+j odd in B (pair index k = i+j-1, weight 2^(32(k+1))), so every product is
+    // one mad.lo.cc/madc.hi.cc pair on an aligned pair and each row is an unbroken carry chain; T = A + (B << 32).
+    template <int H>
+    KZG_DI static void mul_half(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+        constexpr int M = 2 * H;
+        uint32_t A[M], B[M];
+#pragma unroll
+        for (int k = 0; k < M; k++) { A[k] = 0; B[k] = 0; }
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            {
+                int klast = -1;
+#pragma unroll
+                for (int j = (i & 1); j < H; j += 2) {
+                    const int k = i + j;
+                    if (klast < 0) A[k] = mad_lo_cc(a[j], b[i], A[k]);
+                    else A[k] = madc_lo_cc(a[j], b[i], A[k]);
+                    A[k + 1] = madc_hi_cc(a[j], b[i], A[k + 1]);
+                    klast = k;
+                }
+                // the carry out of the row lands on a limb that holds at most one earlier carry bit
+                if (klast >= 0 && klast + 2 < M) A[klast + 2] = addc(A[klast + 2], 0);
+            }
+            {
+                int klast = -1;
+#pragma unroll
+                for (int j = 1 - (i & 1); j < H; j += 2) {
+                    const int k = i + j - 1;
+                    if (klast < 0) B[k] = mad_lo_cc(a[j], b[i], B[k]);
+                    else B[k] = madc_lo_cc(a[j], b[i], B[k]);
+                    B[k + 1] = madc_hi_cc(a[j], b[i], B[k + 1]);
+                    klast = k;
+                }
+                if (klast >= 0 && klast + 2 < M) B[klast + 2] = addc(B[klast + 2], 0);
+            }
+        }
+        T[0] = A[0];
+        T[1] = add_cc(A[1], B[0]);
+#pragma unroll
+        for (int k = 2; k < M - 1; k++) T[k] = addc_cc(A[k], B[k - 1]);
+        T[M - 1] = addc(A[M - 1], B[M - 2]);
+    }
+    // x = |x0 - x1| over H limbs (x0 = lo[0..H), x1 = hi[0..H)); returns all-ones when x0 < x1
+    template <int H>
+    KZG_DI static uint32_t abs_diff(uint32_t* d, const uint32_t* lo, const uint32_t* hi) {
+        d[0] = sub_cc(lo[0], hi[0]);
+#pragma unroll
+        for (int i = 1; i < H; i++) d[i] = subc_cc(lo[i], hi[i]);
+        const uint32_t s = subc(0, 0);
+        d[0] = sub_cc(d[0] ^ s, s);   // (d ^ s) - s: two's-complement negation when s is all ones
+#pragma unroll
+        for (int i = 1; i < H - 1; i++) d[i] = subc_cc(d[i] ^ s, s);
+        d[H - 1] = subc(d[H - 1] ^ s, s);
+        return s;
+    }
+    // T (2N limbs) = a * b, one Karatsuba level over N/2-limb halves
+    KZG_DI static void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+        constexpr int H = N / 2;
+        uint32_t m[N];
+        uint32_t s;
+        {
+            uint32_t da[H], db[H];
+            const uint32_t sa = abs_diff<H>(da, a, a + H);       // a0 - a1
+            const uint32_t sb = abs_diff<H>(db, b + H, b);       // b1 - b0
+            mul_half<H>(m, da, db);
+            s = sa ^ sb;                                         // all ones: the cross term is -m
+        }
+        mul_half<H>(T, a, b);
+        mul_half<H>(T + N, a + H, b + H);
+        // t = z0 + z2 +- m  (N+1 limbs; the true value a0*b1 + a1*b0 is non-negative)
+        uint32_t t[N + 1];
+        t[0] = add_cc(T[0], T[N]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = addc_cc(T[i], T[N + i]);
+        t[N] = addc(0, 0);
+        (void)add_cc(s, s);                                      // carry flag := s & 1 (the +1 of the negation)
+        t[0] = addc_cc(t[0], m[0] ^ s);
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = addc_cc(t[i], m[i] ^ s);
+        t[N] = addc(t[N], s);                                    // sign extension
+        T[H] = add_cc(T[H], t[0]);
+#pragma unroll
+        for (int i = 1; i <= N; i++) T[H + i] = addc_cc(T[H + i], t[i]);
+#pragma unroll
+        for (int k = H + N + 1; k < 2 * N - 1; k++) T[k] = addc_cc(T[k], 0);
+        T[2 * N - 1] = addc(T[2 * N - 1], 0);
+    }
+    // T (2N limbs, < MOD * 2^(32N)) -> T / 2^(32N) mod MOD.  Only the low N limbs take part in the N word-serial rounds
+    // ((T + M*MOD)/R = (T_lo + M*MOD)/R + T_hi exactly); they run on the interleaved (E, O) frame of mul_inline, where
+    // the carry of the frame shift enters the next round's odd chain, so no round pays a carry ripple.
+    KZG_DI static Fe redc_wide(const uint32_t* T) {
+        uint32_t E[N], O[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { E[j] = T[j]; O[j] = 0; }
+        reduce_step(E, O);
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            uint32_t nE[N], nO[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) nE[j] = O[j];
+            nE[0] = add_cc(nE[0], E[1]);                          // carry -> limb 0 of the new odd frame
+            const uint32_t m = nE[0] * P::inv32();
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                nO[j] = madc_lo_cc(P::mod(j + 1), m, E[j + 2]);
+                nO[j + 1] = madc_hi_cc(P::mod(j + 1), m, E[j + 3]);
+            }
+            nO[N - 2] = madc_lo_cc(P::mod(N - 1), m, 0);
+            nO[N - 1] = madc_hi(P::mod(N - 1), m, 0);
+            nE[0] = mad_lo_cc(P::mod(0), m, nE[0]);
+            nE[1] = madc_hi_cc(P::mod(0), m, nE[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                nE[j] = madc_lo_cc(P::mod(j), m, nE[j]);
+                nE[j + 1] = madc_hi_cc(P::mod(j), m, nE[j + 1]);
+            }
+            nO[N - 1] = addc(nO[N - 1], 0);
+#pragma unroll
+            for (int j = 0; j < N; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+        }
+        // U = E/2^32 + O (<= MOD), result = U + T_hi (< 2 MOD)
+        Fe r;
+        r.l[0] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(E[j + 1], O[j]);
+        r.l[N - 1] = addc(0, O[N - 1]);
+        r.l[0] = add_cc(r.l[0], T[N]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(r.l[j], T[N + j]);
+        r.l[N - 1] = addc(r.l[N - 1], T[2 * N - 1]);
+        r.final_sub();
+        return r;
+    }
+    KZG_DI static Fe mul_kara(const Fe& a, const Fe& b) {
+        uint32_t T[2 * N];
+        mul_wide(T, a.l, b.l);
+        return redc_wide(T);
+    }
+    // a*b - c*d with one reduction: D = a*b - c*d (+ MOD*2^(32N) when negative) lies in [0, MOD*2^(32N))
+    KZG_DI static Fe mul_sub_mul(const Fe& a, const Fe& b, const Fe& c, const Fe& d) {
+        uint32_t T[2 * N], U[2 * N];
+        mul_wide(T, a.l, b.l);
+        mul_wide(U, c.l, d.l);
+        T[0] = sub_cc(T[0], U[0]);
+#pragma unroll
+        for (int k = 1; k < 2 * N; k++) T[k] = subc_cc(T[k], U[k]);
+        const uint32_t borrow = subc(0, 0);
+        T[N] = add_cc(T[N], P::mod(0) & borrow);
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) T[N + k] = addc_cc(T[N + k], P::mod(k) & borrow);
+        T[2 * N - 1] = addc(T[2 * N - 1], P::mod(N - 1) & borrow);
+        return redc_wide(T);
+    }
+    __device__ __noinline__ static Fe mul_kara_outlined(Fe a, Fe b) { return mul_kara(a, b); }
+    __device__ __noinline__ static Fe mul_sub_mul_outlined(Fe a, Fe b, Fe c, Fe d) { return mul_sub_mul(a, b, c, d); }
 
     // E + O*2^32 += m*MOD with m chosen so that limb 0 of E becomes zero.
     KZG_DI static void reduce_step(uint32_t* E, uint32_t* O) {

@@ -115,6 +115,39 @@ __global__ void __launch_bounds__(256) mb_kernel(uint32_t* out, long long* cycle
             }
         }
         if (a.l[0] == 0x12345678u) out[tid] = b.l[1] ^ c.l[0] ^ d.l[2];
+    } else if constexpr (MODE == 13 || MODE == 15) {
+        Fq a, b;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; }
+        a.l[11] &= 0x0fffffff; b.l[11] &= 0x0fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 4
+            for (int u = 0; u < MB_UNROLL; u++) {
+                if constexpr (MODE == 13) { a = Fq::mul_kara(a, b); b = Fq::mul_kara(b, a); }
+                else { a = Fq::mul_sub_mul(a, b, b, b); b = Fq::mul_sub_mul(b, a, a, a); }   // counts as 2 products each
+            }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
+    } else if constexpr (MODE == 14) {
+        Fr a, b;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; }
+        a.l[7] &= 0x3fffffff; b.l[7] &= 0x3fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 4
+            for (int u = 0; u < MB_UNROLL; u++) { a = Fr::mul_kara(a, b); b = Fr::mul_kara(b, a); }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
+    } else if constexpr (MODE == 16) {
+        Fq a, b;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { a.l[i] = tid + i * y; b.l[i] = tid * 3 + i + z; }
+        a.l[11] &= 0x0fffffff; b.l[11] &= 0x0fffffff;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll 4
+            for (int u = 0; u < MB_UNROLL; u++) { a = Fq::sqr_inline(a) + b; b = Fq::sqr_inline(b) + a; }
+        }
+        if (a.l[0] == 0x12345678u) out[tid] = b.l[1];
     } else if constexpr (MODE == 5) {
         Fr a, b;
 #pragma unroll
@@ -144,7 +177,8 @@ extern "C" {
 
 // mode: 0 IMAD.lo, 1 IMAD.HI, 2 IMAD.WIDE, 3 mad.lo.cc+madc.hi pair, 4 Fq mul chain, 5 Fr mul chain,
 //       6 IADD, 7 IMAD.WIDE+IADD 1:1, 8 DFMA, 9 DFMA+IMAD.WIDE 1:1 (counts DFMA), 10/11 Fq/Fr mul_dfma chain,
-//       12 Fq: one IMAD chain + one DFMA chain per thread, 100 = HBM copy (bytes = iters MiB each way)
+//       12 Fq: one IMAD chain + one DFMA chain per thread, 13/14 Fq/Fr Karatsuba mul chain, 15 Fq lazy a*b - c*d chain
+//       (counted as two products each), 16 Fq dedicated-square chain, 100 = HBM copy (bytes = iters MiB each way)
 // out[0] = ops/s (mode 4/5: field muls/s; mode 100: bytes moved/s), out[1] = ops per SM-clock per SM, out[2] = ms
 int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double* out) {
     KZG_REQUIRE_INIT();
@@ -188,6 +222,7 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
         switch (mode) {
 #define MB_CASE(M) case M: mb_kernel<M><<<blocks, threads, 0, c.stream>>>(d_out, d_cyc, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
             MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10) MB_CASE(11) MB_CASE(12)
+            MB_CASE(13) MB_CASE(14) MB_CASE(15) MB_CASE(16)
 #undef MB_CASE
             default: set_error("kzgb_microbench: bad mode %d", mode); return KZGB_ERR_INVALID_ARG;
         }

@@ -113,7 +113,11 @@ KZG_DI void madd_hot(XYZZ& acc, const Fq& x2, const Fq& y2) {
     acc.zz = acc.zz * PP;
     acc.zzz = acc.zzz * PPP;
     Fq X3 = R.sqr() - PPP - Q.dbl();
+#ifdef KZG_MSM_LAZY_Y
+    acc.y = Fq::mul_sub_mul_outlined(R, Q - X3, acc.y, PPP);   // two wide products, ONE Montgomery reduction
+#else
     acc.y = R * (Q - X3) - acc.y * PPP;
+#endif
     acc.x = X3;
 }
 

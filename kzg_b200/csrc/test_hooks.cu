@@ -6,7 +6,8 @@
 
 namespace kzg {
 
-// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a), 6 sqr(a), 7 inv_fermat(a), 8 mul via the FP64 pipe
+// op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a), 6 sqr(a), 7 inv_fermat(a), 8 mul via the FP64 pipe,
+//     9 Karatsuba mul, 10/11 lazy-reduction a*b - c*d
 template <class F>
 __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b, F* __restrict__ o, size_t n, int op) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -21,6 +22,9 @@ __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b
         case 5: r = x.from_mont(); break;
         case 7: r = x.inv_fermat(); break;
         case 8: r = F::mul_dfma(x, y); break;
+        case 9: r = F::mul_kara(x, y); break;                      // Karatsuba product + ripple-free reduction
+        case 10: r = F::mul_sub_mul(x, y, x + y, y); break;        // lazy reduction: x*y - (x+y)*y = -y^2
+        case 11: r = F::mul_sub_mul(x, y, y, x.sqr()); break;      // x*y - y*x^2
         default: r = x.sqr(); break;
     }
     o[i] = r;
@@ -33,7 +37,7 @@ static int fe_binop(const void* a, const void* b, void* out, size_t n, int op) {
     std::lock_guard<std::recursive_mutex> g(c.mu);
     use_stream(ctx().stream);
     if (n == 0) return KZGB_OK;
-    if (!a || !out || ((op <= 2 || op == 8) && !b)) {
+    if (!a || !out || ((op <= 2 || (op >= 8 && op <= 11)) && !b)) {
         set_error("test binop: null pointer");
         return KZGB_ERR_INVALID_ARG;
     }

@@ -1,0 +1,125 @@
+// field_host_model.cpp -- host-side bit-exactness check of the limb-level multiplication schedules in
+// kzg_b200/csrc/field.cuh (Karatsuba wide product, ripple-free word-serial reduction, lazy a*b - c*d, dedicated
+// squaring).  The routines are the SAME template code the GPU runs, compiled for the host with the PTX carry flag
+// emulated (KZG_HOST_EMU); the model they are compared with is an independent 64-bit-limb CIOS Montgomery product.
+// Test infrastructure only (run by tests/test_field_host_model.py); never linked into libkzg_b200.so.
+#define KZG_HOST_EMU 1
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../kzg_b200/csrc/field.cuh"
+
+using namespace kzg;
+typedef unsigned __int128 u128;
+
+static uint64_t rng_state = 0x9e3779b97f4a7c15ULL;
+static uint64_t rnd() {  // splitmix64
+    uint64_t z = (rng_state += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+template <class P>
+struct Model {
+    static constexpr int N = P::N, W = P::N / 2;
+    static void mod64(uint64_t* m) { for (int i = 0; i < W; i++) m[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32); }
+    static uint64_t inv64() {  // -mod^-1 mod 2^64 by Newton iteration
+        uint64_t m[W]; mod64(m);
+        uint64_t x = 1;
+        for (int i = 0; i < 7; i++) x *= 2 - m[0] * x;
+        return 0 - x;
+    }
+    static bool geq(const uint64_t* a, const uint64_t* b) {
+        for (int i = W - 1; i >= 0; i--) if (a[i] != b[i]) return a[i] > b[i];
+        return true;
+    }
+    static void sub(uint64_t* a, const uint64_t* b) {
+        u128 bw = 0;
+        for (int i = 0; i < W; i++) { u128 t = (u128)a[i] - b[i] - (uint64_t)bw; a[i] = (uint64_t)t; bw = (t >> 64) & 1; }
+    }
+    // r = a*b/2^(64W) mod m (CIOS)
+    static void mul(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+        uint64_t m[W]; mod64(m);
+        const uint64_t inv = inv64();
+        uint64_t t[W + 2];
+        memset(t, 0, sizeof(t));
+        for (int i = 0; i < W; i++) {
+            u128 c = 0;
+            for (int j = 0; j < W; j++) { c += (u128)a[j] * b[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[W]; t[W] = (uint64_t)c; t[W + 1] = (uint64_t)(c >> 64);
+            uint64_t q = t[0] * inv;
+            c = ((u128)q * m[0] + t[0]) >> 64;
+            for (int j = 1; j < W; j++) { c += (u128)q * m[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[W]; t[W - 1] = (uint64_t)c; t[W] = t[W + 1] + (uint64_t)(c >> 64);
+        }
+        if (t[W] || geq(t, m)) sub(t, m);
+        memcpy(r, t, 8 * W);
+    }
+    static void submod(uint64_t* r, const uint64_t* a, const uint64_t* b) {  // a - b mod m
+        uint64_t m[W]; mod64(m);
+        memcpy(r, a, 8 * W);
+        if (!geq(r, b)) {  // r += m first (may wrap past 2^(64W) only transiently: do it as r - b + m in wide arithmetic)
+            u128 c = 0;
+            for (int i = 0; i < W; i++) { c += (u128)r[i] + m[i]; r[i] = (uint64_t)c; c >>= 64; }
+        }
+        sub(r, b);
+    }
+};
+
+template <class P>
+static void random_fe(Fe<P>& x, int kind) {
+    constexpr int N = P::N;
+    uint64_t m[N / 2]; Model<P>::mod64(m);
+    for (;;) {
+        uint64_t v[N / 2];
+        for (int i = 0; i < N / 2; i++) v[i] = rnd();
+        if (kind == 1) for (int i = 0; i < N / 2; i++) v[i] = 0;                         // zero
+        if (kind == 2) { memcpy(v, m, sizeof(v)); v[0] -= 1; }                           // p - 1
+        if (kind == 3) for (int i = N / 4; i < N / 2; i++) v[i] = v[i - N / 4];            // a0 == a1 (zero cross difference)
+        if (kind == 4) for (int i = 0; i < N / 2; i++) v[i] = (rnd() & 1) ? ~0ULL : 0ULL;  // long carry runs
+        if (kind == 5) { for (int i = 0; i < N / 2; i++) v[i] = 0; v[0] = 1; }            // one
+        v[N / 2 - 1] &= (~0ULL) >> (64 - (Fe<P>::bits() - 64 * (N / 2 - 1)));
+        if (Model<P>::geq(v, m)) { if (kind == 2 || kind == 1 || kind == 5) { } else continue; }
+        if (Model<P>::geq(v, m)) continue;
+        memcpy(x.l, v, sizeof(v));
+        return;
+    }
+}
+
+template <class P>
+static int run(const char* name, int iters) {
+    typedef Fe<P> F;
+    constexpr int W = P::N / 2;
+    int bad = 0;
+    for (int it = 0; it < iters && bad < 5; it++) {
+        F a, b, c, d;
+        int k = it < 64 ? it % 8 : 0;
+        random_fe<P>(a, k % 6); random_fe<P>(b, (k / 2) % 6); random_fe<P>(c, (it < 64) ? (it / 8) % 6 : 0); random_fe<P>(d, 0);
+        if (it % 7 == 3) c = a;           // a*b - a*d and a*b - a*b (exact zero / negative differences)
+        if (it % 11 == 5) { c = a; d = b; }
+        uint64_t ma[W], mb[W], mc[W], md[W], ab[W], cd[W], df[W], aa[W];
+        memcpy(ma, a.l, 8 * W); memcpy(mb, b.l, 8 * W); memcpy(mc, c.l, 8 * W); memcpy(md, d.l, 8 * W);
+        Model<P>::mul(ab, ma, mb);
+        Model<P>::mul(cd, mc, md);
+        Model<P>::mul(aa, ma, ma);
+        Model<P>::submod(df, ab, cd);
+        F r0 = F::mul_inline(a, b);     // validates the emulation itself against the model
+        F r1 = F::mul_kara(a, b);
+        F r2 = F::mul_sub_mul(a, b, c, d);
+        F r3 = F::sqr_inline(a);
+        if (memcmp(r0.l, ab, 8 * W)) { printf("%s: mul_inline mismatch at %d\n", name, it); bad++; }
+        if (memcmp(r1.l, ab, 8 * W)) { printf("%s: mul_kara mismatch at %d\n", name, it); bad++; }
+        if (memcmp(r2.l, df, 8 * W)) { printf("%s: mul_sub_mul mismatch at %d\n", name, it); bad++; }
+        if (memcmp(r3.l, aa, 8 * W)) { printf("%s: sqr_inline mismatch at %d\n", name, it); bad++; }
+    }
+    printf("%s: %d iterations, %d mismatches\n", name, iters, bad);
+    return bad;
+}
+
+int main(int argc, char** argv) {
+    int iters = argc > 1 ? atoi(argv[1]) : 200000;
+    int bad = run<FqParams>("Fq", iters) + run<FrParams>("Fr", iters);
+    return bad ? 1 : 0;
+}
