@@ -26,11 +26,16 @@
  * speed).  `_dev` entry points take device pointers (same layouts) and enqueue
  * on the caller-supplied CUDA stream (a cudaStream_t passed as void*; NULL =
  * the CUDA default stream) without synchronising, except where a status must
- * be read back (the witness calls).  Scratch arenas are shared between calls:
- * when consecutive calls use different streams the earlier stream is drained
- * first.  One process drives one GPU (kzgb_init(device)).  Calls are
- * serialised per process by an internal mutex (the reference's provers are
- * Send + Sync; concurrent callers are safe, not parallel).
+ * be read back (the witness calls).  One process drives one GPU
+ * (kzgb_init(device)); every entry point selects that device on the calling
+ * thread for the duration of the call and restores the caller's.
+ * Thread safety (the reference's provers are Send + Sync plain structs,
+ * coeff_form.rs:37-41): any entry point may be called from any host thread.
+ * A call runs on one of a small pool of lanes (stream + scratch arenas), so
+ * calls from different threads overlap on the device; calls that use the SAME
+ * kzgb_srs handle serialise on that handle's lock (its work area is per
+ * handle).  Arenas and work areas are reused between calls: when consecutive
+ * users run on different streams the earlier stream is drained first.
  */
 #ifndef KZG_B200_H
 #define KZG_B200_H
@@ -218,6 +223,43 @@ KZGB_API int kzgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[64
 KZGB_API int kzgb_peer_open(const unsigned char handle[64], void** d_ptr);
 KZGB_API int kzgb_peer_close(void* d_ptr);
 KZGB_API int kzgb_peer_free(void* d_ptr);
+
+/* ---- multi-GPU entry points (one process per GPU on one NVLink/NVSwitch node; NCCL bound at run time) ---------------
+ * SURVEY 8(e) / north_star: the MSM shards by points with the per-GPU partial sums reduced over NCCL; NTTs >= 2^24 use
+ * the four-step split.  Every rank of the job makes the same sequence of calls.  Bring-up: rank 0 calls
+ * kzgb_comm_unique_id and ships the 128 bytes to the other ranks (any transport the host program has: MPI, a file, a
+ * broadcast of its own launcher); every rank then calls kzgb_comm_init after kzgb_init(local device).  With world == 1
+ * (or no communicator) the sharded entry points degenerate to their single-GPU twins. */
+#define KZGB_COMM_ID_BYTES 128
+KZGB_API int kzgb_comm_unique_id(unsigned char id[KZGB_COMM_ID_BYTES]);
+KZGB_API int kzgb_comm_init(int rank, int world, const unsigned char id[KZGB_COMM_ID_BYTES]);
+KZGB_API int kzgb_comm_destroy(void);
+KZGB_API int kzgb_comm_rank(void);
+KZGB_API int kzgb_comm_world(void);
+KZGB_API int kzgb_comm_barrier(void* stream); /* stream-ordered (a 4-byte all-reduce): no host synchronisation */
+/* KZGProver::commit (coeff_form.rs:59-64) over a point-sharded SRS: `shard` holds gs[lo_g, hi_g) (built by this rank
+ * with kzgb_srs_create_* / kzgb_srs_generate(first = lo_g)), `scalars` the matching slice coeffs[lo_g, hi_g).  Every
+ * rank receives the full result.  Exchange: one all-gather of world x 192 B. */
+KZGB_API int kzgb_msm_g1_sharded(kzgb_srs* shard, const kzgb_fr* scalars, size_t m, kzgb_p1_affine* out);
+KZGB_API int kzgb_msm_g1_sharded_dev(kzgb_srs* shard, const void* d_scalars, size_t m, void* d_out, int out_mode, void* stream);
+/* `count` sharded commits in one call (local MSMs pipelined as in kzgb_msm_g1_batch, ONE all-gather of all partials) */
+KZGB_API int kzgb_msm_g1_sharded_batch(kzgb_srs* shard, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
+                                       kzgb_p1_affine* out);
+KZGB_API int kzgb_msm_g1_sharded_batch_dev(kzgb_srs* shard, const void* const* d_scalars, const size_t* ms, size_t count,
+                                           void* d_out, int out_mode, void* stream);
+/* EvaluationDomain::fft / ifft (ft.rs:111-140) of ONE 2^log_n vector split over the ranks: four-step with the
+ * exchange fused into the column pass (peer stores over NVLink into IPC-mapped row matrices, one stream-ordered
+ * barrier, row pass).  The plan owns the peer-mapped matrices; create/destroy are collective.  log_n1 = 0: automatic.
+ * Layouts: input slab [N1][C] with slab[i1][c] = a[i1*N2 + rank*C + c], C = N2/world; result block [N1/world][N2] with
+ * rows[r][k2] = X[(rank*N1/world + r) + N1*k2]. */
+typedef struct kzgb_ntt4_plan kzgb_ntt4_plan;
+KZGB_API int kzgb_ntt4_plan_create(uint32_t log_n, uint32_t log_n1, kzgb_ntt4_plan** out);
+KZGB_API int kzgb_ntt4_plan_destroy(kzgb_ntt4_plan* plan);
+KZGB_API int kzgb_ntt4_plan_shape(const kzgb_ntt4_plan* plan, uint32_t* log_n1, uint32_t* log_n2, uint32_t* log_c);
+KZGB_API int kzgb_ntt_fr_sharded_dev(kzgb_ntt4_plan* plan, const void* d_slab, int inverse, void** d_rows_out, void* stream);
+/* host vectors in natural order (every rank passes the full input; gather != 0: every rank receives the full output,
+ * else only its own elements of `out` are written) */
+KZGB_API int kzgb_ntt_fr_sharded(kzgb_ntt4_plan* plan, const kzgb_fr* in, kzgb_fr* out, int inverse, int gather);
 
 /* ---- EvaluationDomain helpers off the prover path: element-wise passes and the coset transforms.
  * op 0: a[i] *= b[i]  (mul_assign, ft.rs:220-244)      op 1: a[i] -= b[i]  (sub_assign, ft.rs:247-271)

@@ -13,7 +13,6 @@
 
 using namespace kzg;
 
-#define KZG_LOCK() std::lock_guard<std::recursive_mutex> _g(ctx().mu)
 
 static cudaStream_t pick_stream(void* stream) { return use_stream((cudaStream_t)stream); }
 
@@ -21,13 +20,13 @@ extern "C" {
 
 KZGB_API int kzgb_srs_create_g1(const kzgb_p1* points, size_t n, int window_bits, kzgb_srs** out) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (!points || !out) { set_error("kzgb_srs_create_g1: null argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_srs* s = nullptr;
     int st = srs_alloc(&s, n, window_bits);
     if (st) return st;
-    cudaStream_t stream = ctx().stream;
+    cudaStream_t stream = lane().stream;
     void* d_jac = nullptr;
     cudaError_t e = cudaMalloc(&d_jac, n * sizeof(kzgb_p1));
     if (e != cudaSuccess) { srs_free(s); return cuda_fail(e, "cudaMalloc(jacobian staging)", __FILE__, __LINE__); }
@@ -49,13 +48,13 @@ KZGB_API int kzgb_srs_create_g1(const kzgb_p1* points, size_t n, int window_bits
 KZGB_API int kzgb_srs_create_g1_affine(const kzgb_p1_affine* points, size_t n, int window_bits, int on_device,
                                        kzgb_srs** out) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (!points || !out) { set_error("kzgb_srs_create_g1_affine: null argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_srs* s = nullptr;
     int st = srs_alloc(&s, n, window_bits);
     if (st) return st;
-    cudaStream_t stream = ctx().stream;
+    cudaStream_t stream = lane().stream;
     cudaError_t e = cudaMemcpyAsync(s->table, points, n * sizeof(kzgb_p1_affine),
                                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) { srs_free(s); return cuda_fail(e, "copy srs", __FILE__, __LINE__); }
@@ -67,10 +66,14 @@ KZGB_API int kzgb_srs_create_g1_affine(const kzgb_p1_affine* points, size_t n, i
 }
 
 KZGB_API int kzgb_srs_destroy(kzgb_srs* s) {
-    KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
-    cudaDeviceSynchronize();
+    if (!s) return KZGB_OK;
+    // after kzgb_shutdown the handle's device memory is already gone (kzgb_shutdown released it): free the host side
+    if (s->dead || !ctx().initialised) { srs_free(s); return KZGB_OK; }
+    KZG_ENTER();
+    {   // wait for the calls that still use this handle (other threads, or device work it has in flight)
+        KZG_LOCK_SRS(s);
+        if (s->have_last) cudaStreamSynchronize(s->last_stream);
+    }
     srs_free(s);
     return KZGB_OK;
 }
@@ -84,10 +87,11 @@ KZGB_API const void* kzgb_srs_device_points(const kzgb_srs* s) { return s ? s->t
 
 KZGB_API int kzgb_srs_read_affine(const kzgb_srs* s, size_t start, size_t count, kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
-    if (!s || !out || start + count > s->n) { set_error("kzgb_srs_read_affine: bad range"); return KZGB_ERR_INVALID_ARG; }
-    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
+    KZG_ENTER();
+    use_stream(lane().stream);
+    if (!s || !out || start + count > s->n || s->dead) { set_error("kzgb_srs_read_affine: bad range"); return KZGB_ERR_INVALID_ARG; }
+    KZG_LOCK_SRS(s);
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     KZG_CUDA(cudaMemcpy(out, (const kzgb_p1_affine*)s->table + start, count * sizeof(kzgb_p1_affine),
                         cudaMemcpyDeviceToHost));
     return KZGB_OK;
@@ -96,11 +100,12 @@ KZGB_API int kzgb_srs_read_affine(const kzgb_srs* s, size_t start, size_t count,
 // out_mode: 0 affine (96 B), 1 Jacobian (144 B), 2 raw XYZZ partial (192 B, for multi-GPU combine)
 KZGB_API int kzgb_msm_g1_dev(kzgb_srs* s, const void* d_scalars, size_t m, void* d_out, int out_mode, void* stream) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
+    KZG_ENTER();
     if (!s || (!d_scalars && m) || !d_out || out_mode < 0 || out_mode > 2) {
         set_error("kzgb_msm_g1_dev: bad argument");
         return KZGB_ERR_INVALID_ARG;
     }
+    KZG_LOCK_SRS(s);
     cudaStream_t st = pick_stream(stream);
     const XYZZ* res = nullptr;
     int rc = msm_run(s, d_scalars, m, st, &res);
@@ -110,22 +115,22 @@ KZGB_API int kzgb_msm_g1_dev(kzgb_srs* s, const void* d_scalars, size_t m, void*
 
 static int msm_host(kzgb_srs* s, const kzgb_fr* scalars, size_t m, void* out, int mode, size_t out_bytes) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (!s || (!scalars && m) || !out) { set_error("kzgb_msm_g1: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (m > s->n) { set_error("kzgb_msm_g1: %zu scalars > %zu SRS points", m, s->n); return KZGB_ERR_INVALID_ARG; }
-    Context& c = ctx();
+    KZG_LOCK_SRS(s);
     size_t bytes = m * sizeof(kzgb_fr);
     char* d = (char*)staging_reserve(bytes + 256);
     if (!d) return KZGB_ERR_CUDA;
-    if (m) KZG_CUDA(cudaMemcpyAsync(d + 256, scalars, bytes, cudaMemcpyHostToDevice, c.stream));
+    if (m) KZG_CUDA(cudaMemcpyAsync(d + 256, scalars, bytes, cudaMemcpyHostToDevice, lane().stream));
     const XYZZ* res = nullptr;
-    int rc = msm_run(s, d + 256, m, c.stream, &res);
+    int rc = msm_run(s, d + 256, m, lane().stream, &res);
     if (rc) return rc;
-    rc = msm_finish(res, d, mode, c.stream);
+    rc = msm_finish(res, d, mode, lane().stream);
     if (rc) return rc;
-    KZG_CUDA(cudaMemcpyAsync(out, d, out_bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(out, d, out_bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 
@@ -148,66 +153,10 @@ KZGB_API int kzgb_msm_g1_jacobian(kzgb_srs* s, const kzgb_fr* scalars, size_t m,
 // Events hand the slot (staging + work area) back once the tail of item i is done; item i+2 waits for it.
 // Results are identical to `count` separate calls.
 namespace {
-struct MsmPipe {
-    bool ready = false;
-    cudaStream_t heavy, copy, tail_s[2];
-    cudaEvent_t handoff[2], done[2], staged[2];
-    void* d_stage[2] = {nullptr, nullptr};
-    size_t stage_bytes[2] = {0, 0};
-    void* d_out = nullptr;      // count x 192 B device results (host variant)
-    size_t out_bytes = 0;
-    void* h_out = nullptr;      // pinned mirror of d_out
-    bool used[2] = {false, false};  // done[k] has been recorded at least once
-};
-MsmPipe g_pipe;
-
-int pipe_init() {
-    if (g_pipe.ready) return KZGB_OK;
-    int lo = 0, hi = 0;  // lo = least priority (numerically greatest), hi = greatest priority
-    KZG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.heavy, cudaStreamNonBlocking, lo));
-    KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.copy, cudaStreamNonBlocking, lo));
-    for (int k = 0; k < 2; k++) {
-        KZG_CUDA(cudaStreamCreateWithPriority(&g_pipe.tail_s[k], cudaStreamNonBlocking, hi));
-        KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.handoff[k], cudaEventDisableTiming));
-        KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.done[k], cudaEventDisableTiming));
-        KZG_CUDA(cudaEventCreateWithFlags(&g_pipe.staged[k], cudaEventDisableTiming));
-    }
-    g_pipe.ready = true;
-    return KZGB_OK;
-}
-
-}  // namespace
-
-extern "C++" {
-namespace kzg {
-// called by kzgb_shutdown: streams, events and buffers of the batch pipeline
-void msm_pipe_shutdown() {
-    if (!g_pipe.ready) return;
-    cudaStreamSynchronize(g_pipe.heavy);
-    cudaStreamSynchronize(g_pipe.copy);
-    for (int k = 0; k < 2; k++) {
-        cudaStreamSynchronize(g_pipe.tail_s[k]);
-        cudaStreamDestroy(g_pipe.tail_s[k]);
-        cudaEventDestroy(g_pipe.handoff[k]);
-        cudaEventDestroy(g_pipe.done[k]);
-        cudaEventDestroy(g_pipe.staged[k]);
-        if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
-    }
-    cudaStreamDestroy(g_pipe.heavy);
-    cudaStreamDestroy(g_pipe.copy);
-    if (g_pipe.d_out) cudaFree(g_pipe.d_out);
-    if (g_pipe.h_out) cudaFreeHost(g_pipe.h_out);
-    g_pipe = MsmPipe();
-}
-}  // namespace kzg
-}  // extern "C++"
-
-namespace {
-int pipe_reserve_results(size_t count);   // defined with the many-witness helpers below
+int pipe_reserve_results(MsmPipe& g_pipe, size_t count);   // defined with the many-witness helpers below
 size_t out_size(int mode) { return mode == 0 ? sizeof(kzgb_p1_affine) : (mode == 1 ? sizeof(kzgb_p1) : 192); }
 
-int pipe_drain(int rc) {
+int pipe_drain(MsmPipe& g_pipe, int rc) {
     cudaStream_t all[4] = {g_pipe.copy, g_pipe.heavy, g_pipe.tail_s[0], g_pipe.tail_s[1]};
     for (cudaStream_t st : all) {
         cudaError_t e = cudaStreamSynchronize(st);
@@ -226,8 +175,8 @@ static cudaEvent_t g_dbg_start = nullptr;
 static bool pipe_debug() { static int v = -1; if (v < 0) { const char* e = getenv("KZGB_PIPE_DEBUG"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
 static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
-int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int where,
-                  cudaStream_t after) {
+int msm_batch_run(kzgb_srs* s, MsmPipe& g_pipe, const void* const* scalars, const size_t* ms, size_t count, void* out,
+                  int mode, int where, cudaStream_t after) {
     const bool sc_dev = (where & 1) != 0, out_dev = (where & 2) != 0;
     const size_t osz = out_size(mode);
     const bool dbg = pipe_debug();
@@ -238,7 +187,7 @@ int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, siz
         cudaEventRecord(g_dbg_start, g_pipe.heavy);
     }
     if (!out_dev && count) {
-        int rc = pipe_reserve_results(count);
+        int rc = pipe_reserve_results(g_pipe, count);
         if (rc) return rc;
     }
     for (size_t i = 0; i < count; i++) {
@@ -253,7 +202,7 @@ int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, siz
         if (!sc_dev) {
             const size_t bytes = m * sizeof(kzgb_fr);
             if (g_pipe.stage_bytes[k] < bytes) {
-                int rc = pipe_drain(KZGB_OK);
+                int rc = pipe_drain(g_pipe, KZGB_OK);
                 if (rc) return rc;
                 if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
                 g_pipe.d_stage[k] = nullptr;
@@ -301,8 +250,12 @@ int msm_batch_run(kzgb_srs* s, const void* const* scalars, const size_t* ms, siz
 int msm_batch(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int where,
               cudaStream_t after) {
     const bool out_dev = (where & 2) != 0;
-    int rc = pipe_init();
+    MsmPipe* pp = nullptr;
+    int rc = msm_pipe_get(s, &pp);
     if (rc) return rc;
+    MsmPipe& g_pipe = *pp;
+    // the handle's main work area may still be in use by an earlier single call on another stream
+    if (s->have_last) { KZG_CUDA(cudaStreamSynchronize(s->last_stream)); s->have_last = false; }
     if (after) {  // the heavy stream starts after the work already enqueued on the caller's stream
         cudaEvent_t start_ev;
         KZG_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
@@ -311,9 +264,9 @@ int msm_batch(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t 
         KZG_CUDA(cudaStreamWaitEvent(g_pipe.copy, start_ev, 0));
         cudaEventDestroy(start_ev);
     }
-    rc = msm_batch_run(s, scalars, ms, count, out, mode, where, after);
+    rc = msm_batch_run(s, g_pipe, scalars, ms, count, out, mode, where, after);
     // errors, host output and host scalars (the caller may reuse its buffers on return): wait here
-    if (rc != KZGB_OK || !(out_dev && after) || !(where & 1) || pipe_debug()) rc = pipe_drain(rc);
+    if (rc != KZGB_OK || !(out_dev && after) || !(where & 1) || pipe_debug()) rc = pipe_drain(g_pipe, rc);
     if (pipe_debug() && g_dbg_start) {
         fprintf(stderr, "[kzgb pipe] %zu items: host enqueue done at / accumulate done at / item done at (ms)\n", g_dbg.size());
         for (size_t i = 0; i < g_dbg.size(); i++) {
@@ -334,17 +287,28 @@ int msm_batch(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t 
 }
 }  // namespace
 
+extern "C++" {
+namespace kzg {
+// the pipelined batch for other translation units (comm.cu: sharded batches); the caller holds the handle's lock
+int msm_batch_entry(kzgb_srs* s, const void* const* scalars, const size_t* ms, size_t count, void* out, int mode, int where,
+                    cudaStream_t after) {
+    return msm_batch(s, scalars, ms, count, out, mode, where, after);
+}
+}  // namespace kzg
+}  // extern "C++"
+
 // `count` commits against one SRS: scalars[i] points at ms[i] host scalars, out[i] receives the affine result.
 // Same results as `count` calls of kzgb_msm_g1 (coeff_form.rs:59-64 once per polynomial), pipelined as described above.
 KZGB_API int kzgb_msm_g1_batch(kzgb_srs* s, const kzgb_fr* const* scalars, const size_t* ms, size_t count,
                                kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (!s || (count && (!scalars || !ms || !out))) { set_error("kzgb_msm_g1_batch: null argument"); return KZGB_ERR_INVALID_ARG; }
     for (size_t i = 0; i < count; i++)
         if (ms[i] && !scalars[i]) { set_error("kzgb_msm_g1_batch: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
-    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
+    KZG_LOCK_SRS(s);
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return msm_batch(s, (const void* const*)scalars, ms, count, out, 0, 0, nullptr);
 }
 
@@ -354,13 +318,14 @@ KZGB_API int kzgb_msm_g1_batch(kzgb_srs* s, const kzgb_fr* const* scalars, const
 KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* s, const void* const* d_scalars, const size_t* ms, size_t count, void* d_out,
                                    int out_mode, void* stream) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
+    KZG_ENTER();
     if (!s || out_mode < 0 || out_mode > 2 || (count && (!d_scalars || !ms || !d_out))) {
         set_error("kzgb_msm_g1_batch_dev: bad argument");
         return KZGB_ERR_INVALID_ARG;
     }
     for (size_t i = 0; i < count; i++)
         if (ms[i] && !d_scalars[i]) { set_error("kzgb_msm_g1_batch_dev: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
+    KZG_LOCK_SRS(s);
     cudaStream_t st = pick_stream(stream);
     return msm_batch(s, d_scalars, ms, count, d_out, out_mode, 3, st);
 }
@@ -370,20 +335,21 @@ KZGB_API int kzgb_msm_g1_batch_dev(kzgb_srs* s, const void* const* d_scalars, co
 KZGB_API int kzgb_msm_g1_batch_h2d(kzgb_srs* s, const kzgb_fr* const* scalars, const size_t* ms, size_t count, void* d_out,
                                    int out_mode, void* stream) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
+    KZG_ENTER();
     if (!s || out_mode < 0 || out_mode > 2 || (count && (!scalars || !ms || !d_out))) {
         set_error("kzgb_msm_g1_batch_h2d: bad argument");
         return KZGB_ERR_INVALID_ARG;
     }
     for (size_t i = 0; i < count; i++)
         if (ms[i] && !scalars[i]) { set_error("kzgb_msm_g1_batch_h2d: item %zu is null", i); return KZGB_ERR_INVALID_ARG; }
+    KZG_LOCK_SRS(s);
     cudaStream_t st = pick_stream(stream);
     return msm_batch(s, (const void* const*)scalars, ms, count, d_out, out_mode, 2, st);
 }
 
 // ---- shared pieces of the "many witnesses" entry points (host results; scalars produced on the heavy stream) ----
 namespace {
-int pipe_reserve_results(size_t count) {
+int pipe_reserve_results(MsmPipe& g_pipe, size_t count) {
     if (g_pipe.out_bytes >= count * 192) return KZGB_OK;
     if (count < 256) count = 256;   // pinned allocations are slow (up to 0.1 s): never regrow for a handful of results
     if (g_pipe.d_out) { cudaFree(g_pipe.d_out); cudaFreeHost(g_pipe.h_out); g_pipe.d_out = g_pipe.h_out = nullptr; g_pipe.out_bytes = 0; }
@@ -392,10 +358,10 @@ int pipe_reserve_results(size_t count) {
     g_pipe.out_bytes = count * 192;
     return KZGB_OK;
 }
-int pipe_reserve_stage(size_t bytes) {   // both slots; drains the pipeline when it has to grow
+int pipe_reserve_stage(MsmPipe& g_pipe, size_t bytes) {   // both slots; drains the pipeline when it has to grow
     for (int k = 0; k < 2; k++) {
         if (g_pipe.stage_bytes[k] >= bytes) continue;
-        int rc = pipe_drain(KZGB_OK);
+        int rc = pipe_drain(g_pipe, KZGB_OK);
         if (rc) return rc;
         if (g_pipe.d_stage[k]) cudaFree(g_pipe.d_stage[k]);
         g_pipe.d_stage[k] = nullptr;
@@ -406,7 +372,7 @@ int pipe_reserve_stage(size_t bytes) {   // both slots; drains the pipeline when
     return KZGB_OK;
 }
 // MSM of the m scalars in the slot's stage buffer -> affine result i (device + pinned mirror); releases the slot
-int pipe_msm_item(kzgb_srs* s, int k, size_t m, size_t i) {
+int pipe_msm_item(kzgb_srs* s, MsmPipe& g_pipe, int k, size_t m, size_t i) {
     cudaStream_t ts_ = g_pipe.tail_s[k];
     const XYZZ* res = nullptr;
     int rc = msm_run(s, g_pipe.d_stage[k], m, g_pipe.heavy, &res, k, ts_, g_pipe.handoff[k]);
@@ -435,8 +401,8 @@ __global__ void batch_rem_flag_kernel(const Fr* rem, int* flag) {
 KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys, size_t m,
                                      kzgb_p1_affine* out, int* status) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (!s || !p || n == 0 || (m && (!xs || !ys || !out || !status))) {
         set_error("kzgb_witness_coeff_many: bad argument");
         return KZGB_ERR_INVALID_ARG;
@@ -447,9 +413,13 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
         return KZGB_ERR_INVALID_ARG;
     }
     if (m == 0) return KZGB_OK;
-    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
-    int rc = pipe_init();
+    KZG_LOCK_SRS(s);
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
+    MsmPipe* pp = nullptr;
+    int rc = msm_pipe_get(s, &pp);
     if (rc) return rc;
+    MsmPipe& g_pipe = *pp;
+    if (s->have_last) { KZG_CUDA(cudaStreamSynchronize(s->last_stream)); s->have_last = false; }
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     // staging arena: [p | (x_i, y_i) pairs | remainders | flags]; scan workspace in the scratch arena
     const size_t pb = al(n * 32), xyb = al(m * 64), rb = al(m * 32), fb = al(m * sizeof(int));
@@ -461,7 +431,7 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
     Fr* d_xy = (Fr*)(buf + pb);
     Fr* d_rem = (Fr*)(buf + pb + xyb);
     int* d_flag = (int*)(buf + pb + xyb + rb);
-    if ((rc = pipe_reserve_results(m)) || (rc = pipe_reserve_stage(qn * 32))) return rc;
+    if ((rc = pipe_reserve_results(g_pipe, m)) || (rc = pipe_reserve_stage(g_pipe, qn * 32))) return rc;
     cudaStream_t hs = g_pipe.heavy;
     KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, hs));
     // interleave (x_i, y_i) on the device side: two strided copies
@@ -476,9 +446,9 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
         batch_rem_flag_kernel<<<1, 32, 0, hs>>>(d_rem + i, d_flag + i);
         KZG_LAUNCHED();
         if (n == 1) KZG_CUDA(cudaMemsetAsync(d_q, 0, 32, hs));
-        rc = pipe_msm_item(s, k, qn, i);
+        rc = pipe_msm_item(s, g_pipe, k, qn, i);
     }
-    rc = pipe_drain(rc);
+    rc = pipe_drain(g_pipe, rc);
     if (rc) return rc;
     KZG_CUDA(cudaMemcpy(status, d_flag, m * sizeof(int), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < m; i++) {
@@ -494,8 +464,8 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
 KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uint32_t log_d, const size_t* indices,
                                     size_t m, kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
-    use_stream(ctx().stream);
+    KZG_ENTER();
+    use_stream(lane().stream);
     if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
     const size_t d = (size_t)1 << log_d;
     if (!lagrange_srs || !evals || (m && (!indices || !out)) || d > lagrange_srs->n) {
@@ -505,15 +475,19 @@ KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals
     for (size_t j = 0; j < m; j++)
         if (indices[j] >= d) { set_error("kzgb_witness_eval_many: index %zu out of bounds", indices[j]); return KZGB_ERR_INVALID_ARG; }
     if (m == 0) return KZGB_OK;
-    KZG_CUDA(cudaStreamSynchronize(ctx().stream));
-    int rc = pipe_init();
+    KZG_LOCK_SRS(lagrange_srs);
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
+    MsmPipe* pp = nullptr;
+    int rc = msm_pipe_get(lagrange_srs, &pp);
     if (rc) return rc;
+    MsmPipe& g_pipe = *pp;
+    if (lagrange_srs->have_last) { KZG_CUDA(cudaStreamSynchronize(lagrange_srs->last_stream)); lagrange_srs->have_last = false; }
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char* d_evals = (char*)staging_reserve(al(d * 32));
     if (!d_evals) return KZGB_ERR_CUDA;
     char* ws = (char*)scratch_reserve(al(div_by_omega_workspace_bytes(log_d)) + 256);
     if (!ws) return KZGB_ERR_CUDA;
-    if ((rc = pipe_reserve_results(m)) || (rc = pipe_reserve_stage(d * 32))) return rc;
+    if ((rc = pipe_reserve_results(g_pipe, m)) || (rc = pipe_reserve_stage(g_pipe, d * 32))) return rc;
     cudaStream_t hs = g_pipe.heavy;
     KZG_CUDA(cudaMemcpyAsync(d_evals, evals, d * 32, cudaMemcpyHostToDevice, hs));
     for (size_t j = 0; j < m && rc == KZGB_OK; j++) {
@@ -522,9 +496,9 @@ KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals
         if (log_d == 0) KZG_CUDA(cudaMemsetAsync(g_pipe.d_stage[k], 0, 32, hs));
         else rc = div_by_omega_run((const Fr*)d_evals, log_d, (uint32_t)indices[j], (Fr*)g_pipe.d_stage[k], ws, hs);
         if (rc) break;
-        rc = pipe_msm_item(lagrange_srs, k, d, j);
+        rc = pipe_msm_item(lagrange_srs, g_pipe, k, d, j);
     }
-    rc = pipe_drain(rc);
+    rc = pipe_drain(g_pipe, rc);
     if (rc) return rc;
     for (size_t j = 0; j < m; j++) memcpy(out + j, (char*)g_pipe.h_out + j * 192, sizeof(kzgb_p1_affine));
     return KZGB_OK;
@@ -533,7 +507,7 @@ KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals
 // Multi-GPU combine: `count` raw XYZZ partial sums (192 B each, device) -> one point.
 KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d_out, int out_mode, void* stream) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
+    KZG_ENTER();
     if (!d_partials || !d_out || count == 0) { set_error("kzgb_g1_combine_dev: bad argument"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = pick_stream(stream);
     char* d = (char*)scratch_reserve(256);
@@ -549,7 +523,7 @@ KZGB_API int kzgb_g1_combine_dev(const void* d_partials, uint32_t count, void* d
 KZGB_API int kzgb_g1_combine_batch_dev(const void* d_partials, uint32_t count, uint32_t items, void* d_out, int out_mode,
                                        void* stream) {
     KZG_REQUIRE_INIT();
-    KZG_LOCK();
+    KZG_ENTER();
     if (!d_partials || !d_out || count == 0 || out_mode < 0 || out_mode > 2) {
         set_error("kzgb_g1_combine_batch_dev: bad argument");
         return KZGB_ERR_INVALID_ARG;

@@ -385,9 +385,10 @@ extern "C" {
 // m == 1 (X + (y - x), polynomial.rs:244-247).  Distinct xs required (else KZGB_ERR_INVALID_ARG; the reference panics).
 KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kzgb_fr* r_out, size_t* r_len) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!xs || !ys || !r_out || !r_len || m == 0 || m > 4096) {
         set_error("kzgb_interpolate: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;
@@ -401,16 +402,16 @@ KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kz
     Fr* d_Z = (Fr*)(d + 2 * mb + rb);
     int* d_flag = (int*)(d + 2 * mb + 2 * rb);
     char* ws = d + 2 * mb + 2 * rb + 256;
-    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemsetAsync(d_flag, 0, 4, c.stream));
-    int st = interpolate_run(d_xs, d_ys, m, d_r, d_Z, d_flag, ws, c.stream);
+    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemsetAsync(d_flag, 0, 4, lane().stream));
+    int st = interpolate_run(d_xs, d_ys, m, d_r, d_Z, d_flag, ws, lane().stream);
     if (st) return st;
     size_t len = m == 1 ? 2 : m;
     int flag = 0;
-    KZG_CUDA(cudaMemcpyAsync(r_out, d_r, len * 32, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(r_out, d_r, len * 32, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     if (flag & 2) { set_error("kzgb_interpolate: xs are not distinct"); return KZGB_ERR_INVALID_ARG; }
     *r_len = len;
     return KZGB_OK;
@@ -421,12 +422,14 @@ KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kz
 KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xs, const void* d_ys,
                                       size_t m, void* d_r_out, void* d_out, void* stream) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
+    (void)c;
     if (!srs || !d_p || !d_xs || !d_ys || !d_r_out || !d_out || n == 0 || m == 0 || m > 4096) {
         set_error("kzgb_witness_batched_dev: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;
     }
+    KZG_LOCK_SRS(srs);
     cudaStream_t st = use_stream((cudaStream_t)stream);
     size_t lr = m == 1 ? 2 : m;
     size_t L = n > lr ? n : lr;
@@ -464,13 +467,15 @@ KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, 
 KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys, size_t m,
                                   kzgb_fr* r_out, size_t* r_len, kzgb_p1_affine* w_out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!srs || !p || !xs || !ys || !r_out || !r_len || !w_out || n == 0 || m == 0 || m > 4096) {
         set_error("kzgb_witness_batched: bad argument (1 <= m <= 4096)");
         return KZGB_ERR_INVALID_ARG;
     }
+    KZG_LOCK_SRS(srs);
     size_t pb = al(n * 32), mb = al(m * 32), rb = al((m + 2) * 32);
     char* d = (char*)staging_reserve(pb + 2 * mb + rb + 256);
     if (!d) return KZGB_ERR_CUDA;
@@ -479,10 +484,10 @@ KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, con
     Fr* d_ys = (Fr*)(d + pb + mb);
     Fr* d_r = (Fr*)(d + pb + 2 * mb);
     char* d_out = d + pb + 2 * mb + rb;
-    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, c.stream));
-    int rc = kzgb_witness_batched_dev(srs, d_p, n, d_xs, d_ys, m, d_r, d_out, c.stream);
+    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, lane().stream));
+    int rc = kzgb_witness_batched_dev(srs, d_p, n, d_xs, d_ys, m, d_r, d_out, lane().stream);
     if (rc < 0) return rc;
     size_t len = m == 1 ? 2 : m;
     KZG_CUDA(cudaMemcpy(r_out, d_r, len * 32, cudaMemcpyDeviceToHost));

@@ -93,7 +93,7 @@ extern "C" {
 // op 0: a[i] *= b[i] (mul_assign)   1: a[i] -= b[i] (sub_assign)   2: a[i] *= k^i (distribute_powers)   3: a[i] *= k
 KZGB_API int kzgb_fr_vec_op_dev(int op, void* d_a, const void* d_b, size_t n, const kzgb_fr* k, void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if ((!d_a && n) || ((op == 2 || op == 3) && !k)) { set_error("kzgb_fr_vec_op_dev: bad argument"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
     Fr kk = Fr::zero_host();
@@ -103,9 +103,10 @@ KZGB_API int kzgb_fr_vec_op_dev(int op, void* d_a, const void* d_b, size_t n, co
 
 KZGB_API int kzgb_fr_vec_op(int op, kzgb_fr* a, const kzgb_fr* b, size_t n, const kzgb_fr* k) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if ((!a && n) || ((op == 0 || op == 1) && !b && n) || ((op == 2 || op == 3) && !k)) {
         set_error("kzgb_fr_vec_op: bad argument");
         return KZGB_ERR_INVALID_ARG;
@@ -114,33 +115,34 @@ KZGB_API int kzgb_fr_vec_op(int op, kzgb_fr* a, const kzgb_fr* b, size_t n, cons
     size_t bytes = n * 32, pb = (bytes + 255) & ~(size_t)255;
     char* d = (char*)staging_reserve(2 * pb);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, c.stream));
-    if (op == 0 || op == 1) KZG_CUDA(cudaMemcpyAsync(d + pb, b, bytes, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, lane().stream));
+    if (op == 0 || op == 1) KZG_CUDA(cudaMemcpyAsync(d + pb, b, bytes, cudaMemcpyHostToDevice, lane().stream));
     Fr kk = Fr::zero_host();
     if (k) memcpy(kk.l, k->l, 32);
-    int st = fr_vec_op_run(op, (Fr*)d, (const Fr*)(d + pb), n, kk, c.stream);
+    int st = fr_vec_op_run(op, (Fr*)d, (const Fr*)(d + pb), n, kk, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 
 // EvaluationDomain::coset_fft (ft.rs:168-171) / icoset_fft (ft.rs:173-178) on a host vector
 KZGB_API int kzgb_coset_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!inout) { set_error("kzgb_coset_ntt_fr: null pointer"); return KZGB_ERR_INVALID_ARG; }
     size_t bytes = (size_t)32 << log_n;
     char* d = (char*)staging_reserve(2 * bytes);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, c.stream));
-    int st = coset_ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, c.stream);
+    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, lane().stream));
+    int st = coset_ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 
@@ -149,9 +151,10 @@ KZGB_API int kzgb_coset_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
 KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t nb, kzgb_fr* out, size_t out_capacity,
                            size_t* m_out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!a || !b || !out || !m_out || na == 0 || nb == 0) { set_error("kzgb_poly_mul: bad argument"); return KZGB_ERR_INVALID_ARG; }
     uint32_t log_m = 0;
     while (((size_t)1 << log_m) < na + nb) {
@@ -166,16 +169,16 @@ KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t
     Fr* da = (Fr*)d;
     Fr* db = (Fr*)(d + bytes);
     Fr* tmp = (Fr*)(d + 2 * bytes);
-    KZG_CUDA(cudaMemsetAsync(d, 0, 2 * bytes, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(da, a, na * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(db, b, nb * 32, cudaMemcpyHostToDevice, c.stream));
+    KZG_CUDA(cudaMemsetAsync(d, 0, 2 * bytes, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(da, a, na * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(db, b, nb * 32, cudaMemcpyHostToDevice, lane().stream));
     int st;
-    if ((st = ntt_run(da, tmp, log_m, false, c.stream))) return st;
-    if ((st = ntt_run(db, tmp, log_m, false, c.stream))) return st;
-    if ((st = fr_vec_op_run(0, da, db, m, Fr::zero_host(), c.stream))) return st;
-    if ((st = ntt_run(da, tmp, log_m, true, c.stream))) return st;
-    KZG_CUDA(cudaMemcpyAsync(out, da, bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    if ((st = ntt_run(da, tmp, log_m, false, lane().stream))) return st;
+    if ((st = ntt_run(db, tmp, log_m, false, lane().stream))) return st;
+    if ((st = fr_vec_op_run(0, da, db, m, Fr::zero_host(), lane().stream))) return st;
+    if ((st = ntt_run(da, tmp, log_m, true, lane().stream))) return st;
+    KZG_CUDA(cudaMemcpyAsync(out, da, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     *m_out = m;
     return KZGB_OK;
 }

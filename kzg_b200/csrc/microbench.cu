@@ -182,9 +182,10 @@ extern "C" {
 // out[0] = ops/s (mode 4/5: field muls/s; mode 100: bytes moved/s), out[1] = ops per SM-clock per SM, out[2] = ms
 int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double* out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     cudaEvent_t e0, e1;
     KZG_CUDA(cudaEventCreate(&e0));
     KZG_CUDA(cudaEventCreate(&e1));
@@ -194,13 +195,13 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
         void *a, *b;
         KZG_CUDA(cudaMalloc(&a, bytes));
         KZG_CUDA(cudaMalloc(&b, bytes));
-        KZG_CUDA(cudaMemsetAsync(a, 1, bytes, c.stream));
+        KZG_CUDA(cudaMemsetAsync(a, 1, bytes, lane().stream));
         float best = 1e30f;
         for (int rep = 0; rep < 6; rep++) {
-            KZG_CUDA(cudaEventRecord(e0, c.stream));
-            copy_kernel<<<c.sm_count * 8, 512, 0, c.stream>>>((const uint4*)a, (uint4*)b, bytes / 16);
+            KZG_CUDA(cudaEventRecord(e0, lane().stream));
+            copy_kernel<<<c.sm_count * 8, 512, 0, lane().stream>>>((const uint4*)a, (uint4*)b, bytes / 16);
             KZG_LAUNCHED();
-            KZG_CUDA(cudaEventRecord(e1, c.stream));
+            KZG_CUDA(cudaEventRecord(e1, lane().stream));
             KZG_CUDA(cudaEventSynchronize(e1));
             KZG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
             if (rep > 0 && ms < best) best = ms;
@@ -218,16 +219,16 @@ int kzgb_microbench(int mode, int blocks_per_sm, int threads, int iters, double*
     KZG_CUDA(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
     KZG_CUDA(cudaMalloc(&d_cyc, (size_t)blocks * 8));
     for (int rep = 0; rep < 3; rep++) {
-        KZG_CUDA(cudaEventRecord(e0, c.stream));
+        KZG_CUDA(cudaEventRecord(e0, lane().stream));
         switch (mode) {
-#define MB_CASE(M) case M: mb_kernel<M><<<blocks, threads, 0, c.stream>>>(d_out, d_cyc, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
+#define MB_CASE(M) case M: mb_kernel<M><<<blocks, threads, 0, lane().stream>>>(d_out, d_cyc, iters, 0x9e3779b9u, 0x7f4a7c15u); break;
             MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10) MB_CASE(11) MB_CASE(12)
             MB_CASE(13) MB_CASE(14) MB_CASE(15) MB_CASE(16)
 #undef MB_CASE
             default: set_error("kzgb_microbench: bad mode %d", mode); return KZGB_ERR_INVALID_ARG;
         }
         KZG_LAUNCHED();
-        KZG_CUDA(cudaEventRecord(e1, c.stream));
+        KZG_CUDA(cudaEventRecord(e1, lane().stream));
         KZG_CUDA(cudaEventSynchronize(e1));
         KZG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     }

@@ -673,22 +673,89 @@ int srs_alloc(kzgb_srs** out, size_t n, int c) {
         delete s;
         return KZGB_ERR_INVALID_ARG;
     }
+    // a sorted value is (w*n + i) | sign << 31 (msm_digits_kernel): the table index must stay below 2^31
+    if ((uint64_t)s->nwin * n > ((uint64_t)1 << 31)) {
+        set_error("srs: %d windows x %zu points = %llu table entries exceed the 2^31 the sort payload can index; "
+                  "pass a wider window_bits", s->nwin, n, (unsigned long long)s->nwin * n);
+        delete s;
+        return KZGB_ERR_INVALID_ARG;
+    }
     cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->nwin * n * sizeof(Affine));
     if (e != cudaSuccess) {
         delete s;
         return cuda_fail(e, "cudaMalloc(srs table)", __FILE__, __LINE__);
     }
+    srs_register(s);
     *out = s;
     return KZGB_OK;
 }
 
-void srs_free(kzgb_srs* s) {
-    if (!s) return;
+static void pipe_destroy(MsmPipe* p) {
+    if (!p) return;
+    cudaStream_t all[4] = {p->heavy, p->copy, p->tail_s[0], p->tail_s[1]};
+    for (cudaStream_t st : all)
+        if (st) cudaStreamSynchronize(st);
+    for (int k = 0; k < 2; k++) {
+        if (p->handoff[k]) cudaEventDestroy(p->handoff[k]);
+        if (p->done[k]) cudaEventDestroy(p->done[k]);
+        if (p->staged[k]) cudaEventDestroy(p->staged[k]);
+        if (p->d_stage[k]) cudaFree(p->d_stage[k]);
+    }
+    for (cudaStream_t st : all)
+        if (st) cudaStreamDestroy(st);
+    if (p->d_out) cudaFree(p->d_out);
+    if (p->h_out) cudaFreeHost(p->h_out);
+    delete p;
+}
+
+// Frees everything the handle holds on the device (the caller has made sure nothing is in flight on it).
+void srs_release_device(kzgb_srs* s) {
+    if (!s || s->dead) return;
+    pipe_destroy(s->pipe);
+    s->pipe = nullptr;
     if (s->table) cudaFree(s->table);
     if (s->work) cudaFree(s->work);
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < 2; k++) {
         if (s->pipe_work[k]) cudaFree(s->pipe_work[k]);
+        s->pipe_work[k] = nullptr;
+        s->pipe_work_bytes[k] = 0;
+    }
+    s->table = nullptr;
+    s->work = nullptr;
+    s->work_bytes = 0;
+    s->dead = true;
+}
+
+void srs_free(kzgb_srs* s) {
+    if (!s) return;
+    if (!s->dead) {
+        srs_unregister(s);
+        srs_release_device(s);
+    }
     delete s;
+}
+
+int msm_pipe_get(kzgb_srs* s, MsmPipe** out) {
+    if (!s->pipe) {
+        MsmPipe* p = new MsmPipe();
+        int lo = 0, hi = 0;  // lo = least priority (numerically greatest), hi = greatest priority
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->heavy, cudaStreamNonBlocking, lo);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->copy, cudaStreamNonBlocking, lo);
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+            e = cudaStreamCreateWithPriority(&p->tail_s[k], cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->handoff[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->staged[k], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            pipe_destroy(p);
+            return cuda_fail(e, "batch pipeline streams/events", __FILE__, __LINE__);
+        }
+        s->pipe = p;
+    }
+    *out = s->pipe;
+    return KZGB_OK;
 }
 
 // Layout of the per-SRS work area for an MSM over up to n scalars
@@ -761,21 +828,34 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
         set_error("msm: %zu scalars but the SRS holds %zu points", m, s->n);
         return KZGB_ERR_INVALID_ARG;
     }
+    if (s->dead) { set_error("msm: the SRS handle outlived kzgb_shutdown"); return KZGB_ERR_INVALID_ARG; }
     MsmPlan p;
-    int st = msm_plan(s, m ? m : 1, p);
+    // The work area is laid out for the handle's FULL size, not for this call's m: a prover alternates between
+    // commit (m = n) and create_witness (m = n - 1) on one handle, and a layout per m would free and reallocate the
+    // area in the middle of a pipeline.  It is allocated once per slot and never grows afterwards.
+    int st = msm_plan(s, s->n, p);
+    if (st) return st;
+    const size_t full_bytes = p.bytes;
+    st = msm_plan(s, m ? m : 1, p);
     if (st) return st;
     void*& work = slot < 0 ? s->work : s->pipe_work[slot & 1];
     size_t& work_bytes = slot < 0 ? s->work_bytes : s->pipe_work_bytes[slot & 1];
-    if (p.bytes > work_bytes) {
-        if (work) {
+    if (slot < 0) {   // main work area: the previous call may still be running on another stream
+        if (s->have_last && s->last_stream != stream) KZG_CUDA(cudaStreamSynchronize(s->last_stream));
+        s->last_stream = stream;
+        s->have_last = true;
+    }
+    const size_t want = p.bytes > full_bytes ? p.bytes : full_bytes;
+    if (want > work_bytes) {
+        if (work) {   // only reachable if the layout of a smaller m exceeds the full one (alignment); drain first
             KZG_CUDA(cudaStreamSynchronize(stream));
             if (tail_stream) KZG_CUDA(cudaStreamSynchronize(tail_stream));
             cudaFree(work);
             work = nullptr;
             work_bytes = 0;
         }
-        KZG_CUDA(cudaMalloc(&work, p.bytes));
-        work_bytes = p.bytes;
+        KZG_CUDA(cudaMalloc(&work, want));
+        work_bytes = want;
     }
     char* w = (char*)work;
     XYZZ* result = (XYZZ*)(w + p.off_result);

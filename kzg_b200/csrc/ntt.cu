@@ -96,13 +96,6 @@ KZG_DI Fr twiddle(const Fr* __restrict__ tw, uint32_t e, uint32_t log_n, uint32_
 // handing it to an all-to-all, the epilogue stores element (k1, col) straight into the row matrix of the rank
 // that owns row k1 -- peer memory mapped over NVLink (CUDA IPC) -- at rows[k1 mod rpr][rank*C + col], i.e. already
 // transposed into the layout the row pass wants.  Each (k1, tile) is a contiguous T*32-byte peer store.
-constexpr int NTT_MAX_PEERS = 16;
-struct NttScatter {
-    Fr* peer[NTT_MAX_PEERS];   // rows buffer of every rank (peer[rank] is local)
-    uint32_t log_rpr;          // log2(rows per rank) = log_n1 - log2(world)
-    uint32_t rank, log_world, log_c;
-};
-
 template <bool LAST, bool SCATTER>
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, Fr* out, const Fr* __restrict__ tw,
                                                                NttPassParams p, Fr minv, NttScatter sc) {
@@ -255,11 +248,14 @@ __global__ void ntt_twiddle_kernel(Fr* __restrict__ out, Fr omega, size_t count)
 }
 
 // ---- host side ---------------------------------------------------------------
-static Fr* g_tw[33] = {nullptr};
-
+// Twiddle tables are a per-device cache shared by every lane and stream (Context::ntt_tw): a table is built once, on
+// the requesting stream, and that stream is drained before the pointer is published, so later users on any stream
+// read finished data.
 int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out) {
     if (log_n == 0 || log_n >= 32) { *out = nullptr; return KZGB_OK; }
-    if (!g_tw[log_n]) {
+    Context& c = ctx();
+    std::lock_guard<std::mutex> g(c.cache_mu);
+    if (!c.ntt_tw[log_n]) {
         size_t count = (size_t)1 << (log_n - 1);
         Fr* t = nullptr;
         KZG_CUDA(cudaMalloc((void**)&t, count * sizeof(Fr)));
@@ -267,20 +263,14 @@ int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out) {
         Fr dw;
         memcpy(dw.l, w.l, 32);
         ntt_twiddle_kernel<<<div_up((count + 15) / 16, 128), 128, 0, stream>>>(t, dw, count);
-        ctx().launches++;
+        c.launches++;
         cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) { cudaFree(t); return cuda_fail(e, "twiddle kernel", __FILE__, __LINE__); }
-        g_tw[log_n] = t;
+        c.ntt_tw[log_n] = t;
     }
-    *out = g_tw[log_n];
+    *out = (const Fr*)c.ntt_tw[log_n];
     return KZGB_OK;
-}
-
-void ntt_free_twiddles() {
-    for (int i = 0; i < 33; i++) {
-        if (g_tw[i]) cudaFree(g_tw[i]);
-        g_tw[i] = nullptr;
-    }
 }
 
 struct NttPlan {
@@ -314,13 +304,14 @@ static NttPlan ntt_plan(uint32_t log_n) {
     return pl;
 }
 
-static bool g_ntt_attr_set = false;
 static int ntt_set_attrs() {
-    if (!g_ntt_attr_set) {
+    Context& c = ctx();
+    std::lock_guard<std::mutex> g(c.cache_mu);
+    if (!c.ntt_attr_set) {
         KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         KZG_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        g_ntt_attr_set = true;
+        c.ntt_attr_set = true;
     }
     return KZGB_OK;
 }
@@ -464,8 +455,9 @@ extern "C" {
 
 KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* stream) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
+    (void)c;
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!d_inout) { set_error("kzgb_ntt_fr_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
@@ -482,7 +474,7 @@ KZGB_API int kzgb_ntt_fr_dev(void* d_inout, uint32_t log_n, int inverse, void* s
 KZGB_API int kzgb_ntt4_columns_dev(void* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
                                    int inverse, void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (!d_slab) { set_error("kzgb_ntt4_columns_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
     return ntt_columns_run((Fr*)d_slab, log_n, log_n1, log_c, col_offset, inverse != 0, st);
@@ -496,7 +488,7 @@ KZGB_API int kzgb_ntt4_columns_scatter_dev(const void* d_slab, void* const* peer
                                            uint32_t log_n, uint32_t log_n1, uint32_t log_c, uint32_t col_offset,
                                            int inverse, void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (!d_slab || !peer_rows) { set_error("kzgb_ntt4_columns_scatter_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     uint32_t lw = 0;
     while ((1u << lw) < world) lw++;
@@ -521,7 +513,7 @@ KZGB_API int kzgb_ntt4_columns_scatter_dev(const void* d_slab, void* const* peer
 // ---- peer memory for the fused exchange: plain cudaMalloc + CUDA IPC handles (one process per GPU) ----
 KZGB_API int kzgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[64]) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     if (!d_ptr || !handle || bytes == 0) { set_error("kzgb_peer_alloc: bad argument"); return KZGB_ERR_INVALID_ARG; }
     void* p = nullptr;
@@ -535,7 +527,7 @@ KZGB_API int kzgb_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[64
 }
 KZGB_API int kzgb_peer_open(const unsigned char handle[64], void** d_ptr) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (!d_ptr || !handle) { set_error("kzgb_peer_open: bad argument"); return KZGB_ERR_INVALID_ARG; }
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
@@ -544,14 +536,14 @@ KZGB_API int kzgb_peer_open(const unsigned char handle[64], void** d_ptr) {
 }
 KZGB_API int kzgb_peer_close(void* d_ptr) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     KZG_CUDA(cudaDeviceSynchronize());
     KZG_CUDA(cudaIpcCloseMemHandle(d_ptr));
     return KZGB_OK;
 }
 KZGB_API int kzgb_peer_free(void* d_ptr) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     KZG_CUDA(cudaDeviceSynchronize());
     KZG_CUDA(cudaFree(d_ptr));
     return KZGB_OK;
@@ -560,7 +552,7 @@ KZGB_API int kzgb_peer_free(void* d_ptr) {
 KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t world, uint32_t nrows, uint32_t cols,
                                   void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (!d_recv || !d_rows) { set_error("kzgb_ntt4_unpack_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
     size_t total = (size_t)world * nrows * cols * 2;
@@ -575,7 +567,7 @@ KZGB_API int kzgb_ntt4_unpack_dev(const void* d_recv, void* d_rows, uint32_t wor
 KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint32_t batch, int inverse,
                                 const kzgb_fr* scale, void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!d_inout || (log_n > 10 && !d_tmp)) { set_error("kzgb_ntt_batch_dev: null pointer"); return KZGB_ERR_INVALID_ARG; }
     cudaStream_t st = use_stream((cudaStream_t)stream);
@@ -586,19 +578,20 @@ KZGB_API int kzgb_ntt_batch_dev(void* d_inout, void* d_tmp, uint32_t log_n, uint
 
 KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;
     if (!inout) { set_error("kzgb_ntt_fr: null pointer"); return KZGB_ERR_INVALID_ARG; }
     size_t bytes = (size_t)32 << log_n;
     char* d = (char*)scratch_reserve(2 * bytes);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, c.stream));
-    int st = ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, c.stream);
+    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, lane().stream));
+    int st = ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 

@@ -259,7 +259,7 @@ extern "C" {
 
 KZGB_API int kzgb_fr_stream_dev(void* d_out, uint64_t seed, uint64_t start, size_t n, int mode, void* stream) {
     KZG_REQUIRE_INIT();
-    std::lock_guard<std::recursive_mutex> g(ctx().mu);
+    KZG_ENTER();
     if (!d_out && n) { set_error("kzgb_fr_stream_dev: null output"); return KZGB_ERR_INVALID_ARG; }
     if (n == 0) return KZGB_OK;
     cudaStream_t st = use_stream((cudaStream_t)stream);
@@ -273,9 +273,10 @@ KZGB_API int kzgb_fr_stream_dev(void* d_out, uint64_t seed, uint64_t start, size
 KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, size_t first, size_t count,
                                int window_bits, kzgb_srs** out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!secret || !out || count == 0 || first + count > total || (kind != 0 && kind != 1)) {
         set_error("kzgb_srs_generate: bad argument");
         return KZGB_ERR_INVALID_ARG;
@@ -289,7 +290,7 @@ KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, si
     cudaError_t e = cudaMalloc((void**)&d_sc, count * sizeof(Fr));
     if (e != cudaSuccess) { srs_free(h); return cuda_fail(e, "cudaMalloc(srs scalars)", __FILE__, __LINE__); }
     if (kind == 0) {
-        fr_powers_kernel<<<div_up((count + POW_CHUNK - 1) / POW_CHUNK, 128), 128, 0, c.stream>>>(d_sc, s, first, count);
+        fr_powers_kernel<<<div_up((count + POW_CHUNK - 1) / POW_CHUNK, 128), 128, 0, lane().stream>>>(d_sc, s, first, count);
         c.launches++;
     } else {
         if (total & (total - 1)) {
@@ -313,14 +314,14 @@ KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, si
         Fr d_omega, d_zd;
         memcpy(d_omega.l, omega.l, 32);
         memcpy(d_zd.l, zs_over_d.l, 32);
-        lagrange_scalars_kernel<<<div_up((count + LAG_CHUNK - 1) / LAG_CHUNK, 128), 128, 0, c.stream>>>(
+        lagrange_scalars_kernel<<<div_up((count + LAG_CHUNK - 1) / LAG_CHUNK, 128), 128, 0, lane().stream>>>(
             d_sc, s, d_omega, d_zd, first, count);
         c.launches++;
     }
-    st = fixed_base_mul(d_sc, count, h->table, c.stream);
+    st = fixed_base_mul(d_sc, count, h->table, lane().stream);
     cudaFree(d_sc);
-    if (!st) st = srs_build_table(h, c.stream);
-    if (!st && (e = cudaStreamSynchronize(c.stream)) != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__);
+    if (!st) st = srs_build_table(h, lane().stream);
+    if (!st && (e = cudaStreamSynchronize(lane().stream)) != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__);
     if (st) { srs_free(h); return st; }
     *out = h;
     return KZGB_OK;
@@ -330,9 +331,10 @@ KZGB_API int kzgb_srs_generate(int kind, const kzgb_fr* secret, size_t total, si
 // out[i] = L_i(s)*G for the size-2^log_d domain, natural omega^i order, from mono.gs[0 .. 2^log_d).
 KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* mono, uint32_t log_d, int window_bits, kzgb_srs** out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!mono || !out) { set_error("kzgb_srs_lagrange_from_monomial: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (log_d >= 32) return KZGB_DEGREE_TOO_LARGE;
     const size_t d = (size_t)1 << log_d;
@@ -340,6 +342,7 @@ KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* mono, uint32_t log_
         set_error("kzgb_srs_lagrange_from_monomial: domain 2^%u larger than the SRS (%zu points)", log_d, mono->n);
         return KZGB_ERR_INVALID_ARG;
     }
+    KZG_LOCK_SRS(mono);
     kzgb_srs* h = nullptr;
     int st = srs_alloc(&h, d, window_bits);
     if (st) return st;
@@ -347,13 +350,13 @@ KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* mono, uint32_t log_
     cudaError_t e = cudaMalloc((void**)&work, d * sizeof(XYZZ));
     if (e != cudaSuccess) { srs_free(h); return cuda_fail(e, "cudaMalloc(group ntt)", __FILE__, __LINE__); }
     do {
-        group_bitrev_load_kernel<<<div_up(d, 256), 256, 0, c.stream>>>(mono->table, work, log_d);
+        group_bitrev_load_kernel<<<div_up(d, 256), 256, 0, lane().stream>>>(mono->table, work, log_d);
         c.launches++;
         if (log_d > 0) {
             const Fr* tw = nullptr;
-            if ((st = ntt_get_twiddles(log_d, c.stream, &tw))) break;
+            if ((st = ntt_get_twiddles(log_d, lane().stream, &tw))) break;
             for (uint32_t s = 0; s < log_d; s++) {
-                group_ntt_stage_kernel<<<div_up(d / 2, 128), 128, 0, c.stream>>>(work, log_d, s, tw);
+                group_ntt_stage_kernel<<<div_up(d / 2, 128), 128, 0, lane().stream>>>(work, log_d, s, tw);
                 c.launches++;
             }
             FrHost dinv = fr_host_inv(fr_host_from_u64((uint64_t)d));
@@ -363,14 +366,14 @@ KZGB_API int kzgb_srs_lagrange_from_monomial(const kzgb_srs* mono, uint32_t log_
             FrHost dinv_canon = fr_host_mul(dinv, one_canon);   // out of Montgomery form
             Fr k;
             memcpy(k.l, dinv_canon.l, 32);
-            group_scale_kernel<<<div_up(d, 128), 128, 0, c.stream>>>(work, (uint32_t)d, k);
+            group_scale_kernel<<<div_up(d, 128), 128, 0, lane().stream>>>(work, (uint32_t)d, k);
             c.launches++;
         }
-        xyzz_to_affine_batch_kernel<<<div_up((d + NORM_BATCH - 1) / NORM_BATCH, 128), 128, 0, c.stream>>>(work, h->table, d);
+        xyzz_to_affine_batch_kernel<<<div_up((d + NORM_BATCH - 1) / NORM_BATCH, 128), 128, 0, lane().stream>>>(work, h->table, d);
         c.launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) { st = cuda_fail(e, "group ntt launch", __FILE__, __LINE__); break; }
-        if ((st = srs_build_table(h, c.stream))) break;
-        if ((e = cudaStreamSynchronize(c.stream)) != cudaSuccess) st = cuda_fail(e, "group ntt", __FILE__, __LINE__);
+        if ((st = srs_build_table(h, lane().stream))) break;
+        if ((e = cudaStreamSynchronize(lane().stream)) != cudaSuccess) st = cuda_fail(e, "group ntt", __FILE__, __LINE__);
     } while (0);
     cudaFree(work);
     if (st) { srs_free(h); return st; }

@@ -33,9 +33,10 @@ __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b
 template <class F>
 static int fe_binop(const void* a, const void* b, void* out, size_t n, int op) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(ctx().stream);
+    (void)c;
+    use_stream(lane().stream);
     if (n == 0) return KZGB_OK;
     if (!a || !out || ((op <= 2 || (op >= 8 && op <= 11)) && !b)) {
         set_error("test binop: null pointer");
@@ -44,13 +45,13 @@ static int fe_binop(const void* a, const void* b, void* out, size_t n, int op) {
     size_t bytes = n * sizeof(F);
     char* d = (char*)scratch_reserve(3 * bytes);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, c.stream));
-    if (b) KZG_CUDA(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, c.stream));
-    fe_binop_kernel<F><<<div_up(n, 128), 128, 0, c.stream>>>((const F*)d, b ? (const F*)(d + bytes) : nullptr,
+    KZG_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, lane().stream));
+    if (b) KZG_CUDA(cudaMemcpyAsync(d + bytes, b, bytes, cudaMemcpyHostToDevice, lane().stream));
+    fe_binop_kernel<F><<<div_up(n, 128), 128, 0, lane().stream>>>((const F*)d, b ? (const F*)(d + bytes) : nullptr,
                                                              (F*)(d + 2 * bytes), n, op);
     KZG_LAUNCHED();
-    KZG_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(out, d + 2 * bytes, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 

@@ -114,36 +114,39 @@ extern "C" {
 // affine points (host) -> n x 48 compressed bytes (host)
 KZGB_API int kzgb_g1_compress(const kzgb_p1_affine* points, size_t n, uint8_t* out48) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if ((!points || !out48) && n) { set_error("kzgb_g1_compress: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (n == 0) return KZGB_OK;
     size_t pb = al_w(n * 96);
     char* d = (char*)staging_reserve(pb + al_w(n * 48));
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, points, n * 96, cudaMemcpyHostToDevice, c.stream));
-    g1_compress_kernel<<<div_up(n, 128), 128, 0, c.stream>>>((const Affine*)d, n, (uint8_t*)(d + pb));
+    KZG_CUDA(cudaMemcpyAsync(d, points, n * 96, cudaMemcpyHostToDevice, lane().stream));
+    g1_compress_kernel<<<div_up(n, 128), 128, 0, lane().stream>>>((const Affine*)d, n, (uint8_t*)(d + pb));
     KZG_LAUNCHED();
-    KZG_CUDA(cudaMemcpyAsync(out48, d + pb, n * 48, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(out48, d + pb, n * 48, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 
 // SRS points [start, start+count) as compressed bytes
 KZGB_API int kzgb_srs_export_compressed(const kzgb_srs* s, size_t start, size_t count, uint8_t* out48) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!s || !out48 || start + count > s->n) { set_error("kzgb_srs_export_compressed: bad range"); return KZGB_ERR_INVALID_ARG; }
     if (count == 0) return KZGB_OK;
+    KZG_LOCK_SRS(s);
     uint8_t* d = (uint8_t*)staging_reserve(al_w(count * 48));
     if (!d) return KZGB_ERR_CUDA;
-    g1_compress_kernel<<<div_up(count, 128), 128, 0, c.stream>>>(s->table + start, count, d);
+    g1_compress_kernel<<<div_up(count, 128), 128, 0, lane().stream>>>(s->table + start, count, d);
     KZG_LAUNCHED();
-    KZG_CUDA(cudaMemcpyAsync(out48, d, count * 48, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(out48, d, count * 48, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
 
@@ -171,14 +174,15 @@ static int decompress_to(const uint8_t* in48, size_t n, Affine* d_out, cudaStrea
 // (like blstrs `from_compressed_unchecked`).
 KZGB_API int kzgb_g1_decompress(const uint8_t* in48, size_t n, kzgb_p1_affine* out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if ((!in48 || !out) && n) { set_error("kzgb_g1_decompress: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (n == 0) return KZGB_OK;
     Affine* d_out = (Affine*)scratch_reserve(n * sizeof(Affine));
     if (!d_out) return KZGB_ERR_CUDA;
-    int st = decompress_to(in48, n, d_out, c.stream);
+    int st = decompress_to(in48, n, d_out, lane().stream);
     if (st) return st;
     KZG_CUDA(cudaMemcpy(out, d_out, n * sizeof(Affine), cudaMemcpyDeviceToHost));
     return KZGB_OK;
@@ -187,17 +191,18 @@ KZGB_API int kzgb_g1_decompress(const uint8_t* in48, size_t n, kzgb_p1_affine* o
 // SRS handle straight from a compressed-point file image
 KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if (!in48 || !out) { set_error("kzgb_srs_create_g1_compressed: null argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_srs* h = nullptr;
     int st = srs_alloc(&h, n, window_bits);
     if (st) return st;
-    st = decompress_to(in48, n, h->table, c.stream);
-    if (!st) st = srs_build_table(h, c.stream);
+    st = decompress_to(in48, n, h->table, lane().stream);
+    if (!st) st = srs_build_table(h, lane().stream);
     if (!st) {
-        cudaError_t e = cudaStreamSynchronize(c.stream);
+        cudaError_t e = cudaStreamSynchronize(lane().stream);
         if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__);
     }
     if (st) { srs_free(h); return st; }
@@ -209,23 +214,24 @@ KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int wi
 // non-canonical input, i.e. a value >= r, is rejected)
 KZGB_API int kzgb_fr_bytes_le(const void* in, void* out, size_t n, int to_bytes) {
     KZG_REQUIRE_INIT();
+    KZG_ENTER();
     Context& c = ctx();
-    std::lock_guard<std::recursive_mutex> g(c.mu);
-    use_stream(c.stream);
+    (void)c;
+    use_stream(lane().stream);
     if ((!in || !out) && n) { set_error("kzgb_fr_bytes_le: null argument"); return KZGB_ERR_INVALID_ARG; }
     if (n == 0) return KZGB_OK;
     size_t pb = al_w(n * 32);
     char* d = (char*)staging_reserve(2 * pb + 256);
     if (!d) return KZGB_ERR_CUDA;
     int* d_bad = (int*)(d + 2 * pb);
-    KZG_CUDA(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, c.stream));
-    KZG_CUDA(cudaMemsetAsync(d_bad, 0, 4, c.stream));
-    fr_bytes_kernel<<<div_up(n, 256), 256, 0, c.stream>>>((const Fr*)d, (Fr*)(d + pb), n, to_bytes, d_bad);
+    KZG_CUDA(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemsetAsync(d_bad, 0, 4, lane().stream));
+    fr_bytes_kernel<<<div_up(n, 256), 256, 0, lane().stream>>>((const Fr*)d, (Fr*)(d + pb), n, to_bytes, d_bad);
     KZG_LAUNCHED();
     int bad = 0;
-    KZG_CUDA(cudaMemcpyAsync(out, d + pb, n * 32, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, c.stream));
-    KZG_CUDA(cudaStreamSynchronize(c.stream));
+    KZG_CUDA(cudaMemcpyAsync(out, d + pb, n * 32, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
     if (bad) { set_error("kzgb_fr_bytes_le: non-canonical scalar (>= r)"); return KZGB_ERR_INVALID_ARG; }
     return KZGB_OK;
 }
