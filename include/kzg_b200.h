@@ -186,6 +186,25 @@ KZGB_API int kzgb_witness_eval(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uin
 KZGB_API int kzgb_witness_eval_dev(kzgb_srs* lagrange_srs, const void* d_evals, uint32_t log_d, size_t i, void* d_work,
                                    void* d_out, void* stream);
 
+/* ---- device-resident polynomial / evaluation-vector handles: the reference's provers borrow
+ * &Polynomial (polynomial.rs:24-27) / &EvaluationDomain (ft.rs:17-25) and typically run commit -> create_witness ->
+ * create_witness_batched on the SAME polynomial; a kzgb_poly keeps it in HBM (one H2D at upload), so the per-call
+ * traffic is the opening point in and 96 bytes out.  `n` / `m` = polynomial.num_coeffs() (<= uploaded length). */
+typedef struct kzgb_poly kzgb_poly;
+KZGB_API int kzgb_poly_upload(const kzgb_fr* coeffs, size_t n, kzgb_poly** out);
+KZGB_API int kzgb_poly_free(kzgb_poly* poly);
+KZGB_API size_t kzgb_poly_len(const kzgb_poly* poly);
+KZGB_API const void* kzgb_poly_device_ptr(const kzgb_poly* poly);
+KZGB_API int kzgb_poly_download(kzgb_poly* poly, kzgb_fr* out);
+KZGB_API int kzgb_poly_commit(kzgb_srs* srs, kzgb_poly* poly, size_t m, kzgb_p1_affine* out);            /* coeff_form.rs:59-64, eval_form.rs:114-122 */
+KZGB_API int kzgb_poly_witness(kzgb_srs* srs, kzgb_poly* poly, size_t n, const kzgb_fr* x, const kzgb_fr* y,
+                               kzgb_p1_affine* out);                                                     /* coeff_form.rs:66-81 */
+KZGB_API int kzgb_poly_witness_batched(kzgb_srs* srs, kzgb_poly* poly, size_t n, const kzgb_fr* xs, const kzgb_fr* ys,
+                                       size_t m, kzgb_fr* r_out, size_t* r_len, kzgb_p1_affine* w_out);   /* coeff_form.rs:83-111 */
+KZGB_API int kzgb_poly_witness_eval(kzgb_srs* lagrange_srs, kzgb_poly* evals, uint32_t log_d, size_t i,
+                                    kzgb_p1_affine* out);                                                /* eval_form.rs:124-140 */
+KZGB_API int kzgb_poly_ntt(kzgb_poly* poly, uint32_t log_n, int inverse);                                /* ft.rs:111-140, in place */
+
 /* ---- stage timers (CUDA events on the launching stream; bench.py's roofline) --- */
 KZGB_API int kzgb_profile_enable(int on);
 KZGB_API int kzgb_profile_read(double* sum_ms, uint64_t* counts); /* arrays of kzgb_profile_stage_count() */

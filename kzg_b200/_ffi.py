@@ -510,3 +510,156 @@ def fr_from_bytes_le(data: bytes) -> np.ndarray:
     out = np.zeros_like(a)
     check(lib().kzgb_fr_bytes_le(ptr(a), ptr(out), C.c_size_t(len(a)), C.c_int(0)))
     return out
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU entry points (NCCL inside the library; one process per GPU)
+# ---------------------------------------------------------------------------
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: the 128-byte NCCL id to ship to the other ranks (any transport)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    check(load().kzgb_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(rank: int, world: int, uid: bytes | None) -> None:
+    buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(uid) if uid is not None else None
+    check(lib().kzgb_comm_init(C.c_int(rank), C.c_int(world), buf))
+
+
+def comm_destroy() -> None:
+    check(lib().kzgb_comm_destroy())
+
+
+def comm_barrier(stream: int = 0) -> None:
+    check(lib().kzgb_comm_barrier(C.c_void_p(stream)))
+
+
+def msm_sharded(srs: SRS, scalars) -> np.ndarray:
+    """commit over a point-sharded SRS from host scalars (this rank's slice) -> affine point on every rank."""
+    sc = u64(scalars, (-1, 4))
+    out = np.empty(12, dtype=np.uint64)
+    check(lib().kzgb_msm_g1_sharded(srs._h, ptr(sc), C.c_size_t(len(sc)), ptr(out)))
+    return out
+
+
+def msm_sharded_dev(srs: SRS, d_scalars: int, m: int, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+    check(lib().kzgb_msm_g1_sharded_dev(srs._h, C.c_void_p(d_scalars), C.c_size_t(m), C.c_void_p(d_out), C.c_int(out_mode),
+                                        C.c_void_p(stream)))
+
+
+def msm_sharded_batch(srs: SRS, scalars_list) -> np.ndarray:
+    arrs = [u64(a, (-1, 4)) for a in scalars_list]
+    count = len(arrs)
+    ptrs = (C.c_void_p * max(count, 1))(*[a.ctypes.data if len(a) else None for a in arrs])
+    ms = (C.c_size_t * max(count, 1))(*[len(a) for a in arrs])
+    out = np.zeros((count, 12), dtype=np.uint64)
+    check(lib().kzgb_msm_g1_sharded_batch(srs._h, ptrs, ms, C.c_size_t(count), ptr(out)))
+    return out
+
+
+def msm_sharded_batch_dev(srs: SRS, d_scalars, ms, d_out: int, out_mode: int = 0, stream: int = 0) -> None:
+    count = len(d_scalars)
+    ptrs = (C.c_void_p * max(count, 1))(*[C.c_void_p(int(p)) for p in d_scalars])
+    lens = (C.c_size_t * max(count, 1))(*[int(m) for m in ms])
+    check(lib().kzgb_msm_g1_sharded_batch_dev(srs._h, ptrs, lens, C.c_size_t(count), C.c_void_p(d_out), C.c_int(out_mode),
+                                              C.c_void_p(stream)))
+
+
+class Ntt4Plan:
+    """kzgb_ntt4_plan: the fused four-step NTT of one 2^log_n vector over the communicator's ranks (collective
+    create/close).  Layouts: see include/kzg_b200.h."""
+
+    def __init__(self, log_n: int, log_n1: int = 0):
+        h = C.c_void_p()
+        check(lib().kzgb_ntt4_plan_create(C.c_uint32(log_n), C.c_uint32(log_n1), C.byref(h)))
+        self._h = h
+        self.log_n = log_n
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().kzgb_ntt4_plan_shape(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        self.l1, self.l2, self.lc = int(a.value), int(b.value), int(c.value)
+
+    def run_dev(self, d_slab: int, inverse: bool = False, stream: int = 0) -> int:
+        """Device slab in (only read) -> device pointer of this rank's [N1/world][N2] result block."""
+        rows = C.c_void_p()
+        check(lib().kzgb_ntt_fr_sharded_dev(self._h, C.c_void_p(d_slab), C.c_int(int(inverse)), C.byref(rows), C.c_void_p(stream)))
+        return int(rows.value)
+
+    def run_host(self, vec, inverse: bool = False, gather: bool = True) -> np.ndarray:
+        a = u64(vec, (-1, 4))
+        assert len(a) == 1 << self.log_n
+        out = np.zeros_like(a)
+        check(lib().kzgb_ntt_fr_sharded(self._h, ptr(a), ptr(out), C.c_int(int(inverse)), C.c_int(int(gather))))
+        return out
+
+    def close(self):
+        if self._h is not None:
+            check(lib().kzgb_ntt4_plan_destroy(self._h))
+            self._h = None
+
+
+# ---------------------------------------------------------------------------
+# device-resident polynomial handles (kzgb_poly)
+# ---------------------------------------------------------------------------
+class DevicePoly:
+    """Owns a kzgb_poly*: a coefficient (or evaluation) vector kept in HBM across calls."""
+
+    def __init__(self, coeffs):
+        c = u64(coeffs, (-1, 4))
+        h = C.c_void_p()
+        check(lib().kzgb_poly_upload(ptr(c), C.c_size_t(len(c)), C.byref(h)))
+        self._h = h
+        self.n = len(c)
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.n, 4), dtype=np.uint64)
+        check(lib().kzgb_poly_download(self._h, ptr(out)))
+        return out
+
+    @property
+    def device_ptr(self) -> int:
+        f = lib().kzgb_poly_device_ptr
+        f.restype = C.c_void_p
+        return int(f(self._h) or 0)
+
+    def commit(self, srs: SRS, m: int | None = None) -> np.ndarray:
+        out = np.empty(12, dtype=np.uint64)
+        check(lib().kzgb_poly_commit(srs._h, self._h, C.c_size_t(self.n if m is None else m), ptr(out)))
+        return out
+
+    def witness(self, srs: SRS, n: int, x, y):
+        out = np.zeros(12, dtype=np.uint64)
+        st = check(lib().kzgb_poly_witness(srs._h, self._h, C.c_size_t(n), ptr(u64(x, (4,))), ptr(u64(y, (4,))), ptr(out)))
+        return st, out
+
+    def witness_batched(self, srs: SRS, n: int, xs, ys):
+        xs, ys = u64(xs, (-1, 4)), u64(ys, (-1, 4))
+        m = len(xs)
+        r = np.zeros((max(m, 2), 4), dtype=np.uint64)
+        w = np.zeros(12, dtype=np.uint64)
+        rl = C.c_size_t(0)
+        st = check(lib().kzgb_poly_witness_batched(srs._h, self._h, C.c_size_t(n), ptr(xs), ptr(ys), C.c_size_t(m), ptr(r),
+                                                   C.byref(rl), ptr(w)))
+        return st, r[: rl.value], w
+
+    def witness_eval(self, srs: SRS, log_d: int, i: int) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        check(lib().kzgb_poly_witness_eval(srs._h, self._h, C.c_uint32(log_d), C.c_size_t(i), ptr(out)))
+        return out
+
+    def ntt(self, log_n: int, inverse: bool = False) -> int:
+        return check(lib().kzgb_poly_ntt(self._h, C.c_uint32(log_n), C.c_int(int(inverse))))
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.kzgb_poly_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -40,6 +40,8 @@ class KZGProver:
         if n > len(self._parameters):
             # `&self.parameters.gs[..polynomial.num_coeffs()]` panics (coeff_form.rs:60)
             raise IndexError(f"range end index {n} out of range for slice of length {len(self._parameters)}")
+        if polynomial.device is not None:      # resident copy: no per-call upload (Polynomial.to_device)
+            return polynomial.device.commit(self._parameters.srs, n)
         return self._parameters.srs.msm(polynomial.slice_coeffs())
 
     def commit_many(self, polynomials) -> np.ndarray:
@@ -58,7 +60,10 @@ class KZGProver:
         coeffs = polynomial.slice_coeffs()
         # degree-0 dividends never reach the device: zero -> ([0], None) -> gs[0]*0; non-zero constant ->
         # ([0], Some(self)) -> Err (polynomial.rs:194-199).  The C ABI implements exactly the same rule.
-        st, w = _ffi.witness_coeff(self._parameters.srs, coeffs, x, y)
+        if polynomial.device is not None:
+            st, w = polynomial.device.witness(self._parameters.srs, polynomial.num_coeffs(), x, y)
+        else:
+            st, w = _ffi.witness_coeff(self._parameters.srs, coeffs, x, y)
         if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
             raise PointNotOnPolynomial()
         return w
@@ -81,7 +86,10 @@ class KZGProver:
         xs = _ffi.u64(xs, (-1, 4))
         ys = _ffi.u64(ys, (-1, 4))
         assert len(xs) == len(ys)  # polynomial.rs:242
-        st, r, w = _ffi.witness_batched(self._parameters.srs, polynomial.slice_coeffs(), xs, ys)
+        if polynomial.device is not None:
+            st, r, w = polynomial.device.witness_batched(self._parameters.srs, polynomial.num_coeffs(), xs, ys)
+        else:
+            st, r, w = _ffi.witness_batched(self._parameters.srs, polynomial.slice_coeffs(), xs, ys)
         if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
             raise PointNotOnPolynomial()
         return KZGBatchWitness(Polynomial(r, len(r) - 1), w)

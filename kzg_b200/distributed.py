@@ -44,6 +44,60 @@ def init_process_group_from_env(backend: Optional[str] = None) -> Tuple[int, int
     return rank, world, local
 
 
+# ---------------------------------------------------------------------------
+# C-ABI communicator (NCCL inside libkzg_b200.so): the product path on GPUs.  torch.distributed only carries the
+# 128-byte id during bring-up; the collectives of the data path are issued by the library itself
+# (kzgb_msm_g1_sharded*, kzgb_ntt_fr_sharded*), so a Rust / C++ caller reaches the same code with no Python.
+# ---------------------------------------------------------------------------
+_comm_ready = False
+
+
+def comm_init(group=None) -> Tuple[int, int]:
+    """Initialises the library's communicator for the ranks of `group` (default: the world).  Returns (rank, world)."""
+    global _comm_ready
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if not _comm_ready:
+        uid = [_ffi.comm_unique_id() if (rank == 0 and world > 1) else None]
+        if world > 1:
+            dist.broadcast_object_list(uid, src=0, group=group)
+        _ffi.comm_init(rank, world, uid[0])
+        _comm_ready = True
+    return rank, world
+
+
+def comm_destroy() -> None:
+    global _comm_ready
+    if _comm_ready:
+        _ffi.comm_destroy()
+        _comm_ready = False
+
+
+def commit_sharded(srs_shard, scalars_shard) -> np.ndarray:
+    """KZGProver::commit (coeff_form.rs:59-64) over a point-sharded SRS, host scalars in, affine point out (u64[12])
+    on every rank: kzgb_msm_g1_sharded."""
+    return _ffi.msm_sharded(srs_shard, scalars_shard)
+
+
+def commit_sharded_dev(srs_shard, scalars_shard: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-resident variant: kzgb_msm_g1_sharded_dev on the current stream -> int64[12] affine."""
+    if out is None:
+        out = torch.zeros(12, dtype=torch.int64, device=scalars_shard.device)
+    _ffi.msm_sharded_dev(srs_shard, scalars_shard.data_ptr(), scalars_shard.shape[0], out.data_ptr(), 0,
+                         torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def commit_sharded_many_dev(srs_shard, scalars_shards, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K sharded commits in one call (pipelined local MSMs, one all-gather): kzgb_msm_g1_sharded_batch_dev."""
+    k = len(scalars_shards)
+    if out is None:
+        out = torch.zeros((k, 12), dtype=torch.int64, device=scalars_shards[0].device)
+    _ffi.msm_sharded_batch_dev(srs_shard, [t.data_ptr() for t in scalars_shards], [t.shape[0] for t in scalars_shards],
+                               out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    return out
+
+
 class CudaOps:
     """Local kernels behind the C ABI, operating on torch CUDA tensors (int64 views of the blst layouts)."""
 

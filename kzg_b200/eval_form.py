@@ -60,6 +60,8 @@ class KZGProverEvalForm:
         assert self.d == evals.d
         if len(evals) > len(self.lagrange_basis_g):
             raise IndexError("range end index out of range for slice")  # :117
+        if evals.device is not None:
+            return evals.device.commit(self.lagrange_basis_g, len(evals))
         return self.lagrange_basis_g.msm(evals.coeffs)
 
     def commit_many(self, evals_list) -> np.ndarray:
@@ -75,6 +77,8 @@ class KZGProverEvalForm:
         # eval_form.rs:124-140 (infallible)
         if i >= len(evals.coeffs):
             raise IndexError("index out of bounds")  # evals.coeffs[i], :125
+        if evals.device is not None:
+            return evals.device.witness_eval(self.lagrange_basis_g, evals.exp, i)
         return _ffi.witness_eval(self.lagrange_basis_g, evals.coeffs, evals.exp, i)
 
     def create_witness_many(self, evals: EvaluationDomain, indices) -> np.ndarray:

@@ -34,6 +34,15 @@ class EvaluationDomain:
         self.geninv = pow(7, -1, R_MOD)
         self.minv = pow(d % R_MOD, -1, R_MOD)
 
+    @property
+    def coeffs(self) -> np.ndarray:
+        return self._coeffs
+
+    @coeffs.setter
+    def coeffs(self, value) -> None:
+        self._coeffs = value
+        self.release_device()     # a resident copy of the old values would be stale
+
     @classmethod
     def from_coeffs(cls, coeffs) -> "EvaluationDomain":
         # ft.rs:94-109: pad with zeros to the next power of two
@@ -42,6 +51,24 @@ class EvaluationDomain:
         if m > len(c):
             c = np.vstack([c, np.zeros((m - len(c), 4), dtype=np.uint64)])
         return cls(c, m, exp, omega)
+
+    # ---- device residency ----
+    def to_device(self) -> "EvaluationDomain":
+        """Keeps a copy of the evaluations in HBM (kzgb_poly_upload): KZGProverEvalForm.commit / create_witness then
+        skip the per-call upload.  Host-side mutations (fft, ...) drop the resident copy."""
+        self.release_device()
+        self._dev = _ffi.DevicePoly(self.coeffs)
+        return self
+
+    def release_device(self) -> None:
+        d = getattr(self, "_dev", None)
+        if d is not None:
+            d.close()
+        self._dev = None
+
+    @property
+    def device(self):
+        return getattr(self, "_dev", None)
 
     def __len__(self) -> int:
         return len(self.coeffs)
@@ -55,6 +82,13 @@ class EvaluationDomain:
     def _check(self):
         if len(self.coeffs) != (1 << self.exp):
             raise AssertionError("assertion failed: n == 1 << log_n")  # ft.rs:302
+        # The device transform always uses the canonical 2^exp-th root root_of_unity^(2^(32-exp)) and the scale
+        # 2^-exp (what compute_omega / from_coeffs produce, ft.rs:55-109).  The reference's best_fft would honour ANY
+        # omega / d passed to `new`; a domain built with other parameters must fail loudly here, not transform
+        # silently with different constants.
+        if self.d != (1 << self.exp) or self.omega != pow(ROOT_OF_UNITY, 1 << (FR_S - self.exp), R_MOD):
+            raise ValueError("EvaluationDomain: only the canonical domain (d = 2^exp, omega = compute_omega(d)) is "
+                             "supported by the device transform")
 
     def fft(self) -> None:
         # ft.rs:111-113

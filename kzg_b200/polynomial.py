@@ -46,6 +46,26 @@ class Polynomial:
     def clone(self) -> "Polynomial":
         return Polynomial(self.coeffs.copy(), self.degree)
 
+    # ---- device residency ----
+    def to_device(self) -> "Polynomial":
+        """Uploads the coefficients once (kzgb_poly_upload); commit / create_witness / create_witness_batched of a
+        prover then run on the resident copy instead of re-uploading per call.  The host array stays authoritative for
+        the bookkeeping (degree rules, equality); mutate it and the resident copy is stale -- call `to_device` again."""
+        self.release_device()
+        self._dev = _ffi.DevicePoly(self.coeffs)
+        return self
+
+    def release_device(self) -> None:
+        d = getattr(self, "_dev", None)
+        if d is not None:
+            d.close()
+        self._dev = None
+
+    @property
+    def device(self):
+        """The resident copy (an _ffi.DevicePoly) or None."""
+        return getattr(self, "_dev", None)
+
     def is_zero(self) -> bool:
         # polynomial.rs:45-47
         return self.degree == 0 and _is_zero(self.coeffs[0])

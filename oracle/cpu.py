@@ -165,6 +165,15 @@ def setup_g1(s, n: int) -> np.ndarray:
     return out
 
 
+def setup_g1_fast(s, n: int, first: int = 0, threads: int = 0) -> np.ndarray:
+    """The points of `setup_g1` (gs[i] = s^i*G, i in [first, first+n)) by a threaded fixed-base multiplication:
+    benchmark-size SRS for the CPU baseline arm.  Jacobian, NOT normalised (z != 1)."""
+    import os
+    out = np.zeros((n, 18), dtype=np.uint64)
+    lib().kzgo_setup_g1_fast(_p(out), _p(_u64(s, (4,))), C.c_size_t(first), C.c_size_t(n), C.c_int(threads or (os.cpu_count() or 1)))
+    return out
+
+
 def msm_g1(points, scalars, threads: int = 1) -> np.ndarray:
     points, scalars = _u64(points, (-1, 18)), _u64(scalars, (-1, 4))
     n = min(len(points), len(scalars))

@@ -601,6 +601,58 @@ EXPORT void kzgo_setup_g1(p1_t *gs, const fr_t *s, size_t n) {
     for (size_t i = 1; i < n; i++) p1_mul_canon(&gs[i], &gs[i - 1], k);
 }
 
+/* The SAME points gs[i] = s^i * G (i in [first, first+count)) as kzgo_setup_g1, built in parallel for benchmark-size
+ * inputs of the CPU baseline: scalars s^i by a running product per thread, then a fixed-base windowed multiplication of
+ * G (8-bit windows, 32 x 255 precomputed affine multiples, 32 mixed additions per point).  Checked against the literal
+ * sequential setup in tests/test_oracle.py.  Test/bench infrastructure, not a restatement of reference code. */
+typedef struct { p1_t *gs; const fr_t *s; size_t first, count; int tid, nthreads; const p1a_t *table; } setup_fast_t;
+static void *setup_fast_worker(void *arg) {
+    setup_fast_t *a = (setup_fast_t *)arg;
+    size_t per = (a->count + a->nthreads - 1) / a->nthreads;
+    size_t lo = (size_t)a->tid * per, hi = lo + per;
+    if (hi > a->count) hi = a->count;
+    if (lo >= hi) return NULL;
+    fr_t cur;
+    fr_pow_u64(&cur, a->s, (uint64_t)(a->first + lo));
+    for (size_t i = lo; i < hi; i++) {
+        uint64_t k[4];
+        fr_to_canonical(k, &cur);
+        p1_t acc;
+        p1_set_inf(&acc);
+        for (int w = 0; w < 32; w++) {
+            uint32_t d = (uint32_t)((k[w >> 3] >> ((w & 7) * 8)) & 0xff);
+            if (d) p1_add_affine(&acc, &acc, &a->table[w * 255 + (d - 1)]);
+        }
+        a->gs[i] = acc;
+        fr_mul(&cur, &cur, a->s);
+    }
+    return NULL;
+}
+EXPORT void kzgo_setup_g1_fast(p1_t *gs, const fr_t *s, size_t first, size_t count, int threads) {
+    if (threads < 1) threads = 1;
+    if (count == 0) return;
+    /* table[w][d-1] = d * 2^(8w) * G, affine */
+    p1_t *jt = (p1_t *)malloc(sizeof(p1_t) * 32 * 255);
+    p1a_t *table = (p1a_t *)malloc(sizeof(p1a_t) * 32 * 255);
+    p1_t base;
+    kzgo_g1_generator(&base);
+    for (int w = 0; w < 32; w++) {
+        jt[w * 255] = base;
+        for (int d = 1; d < 255; d++) p1_add(&jt[w * 255 + d], &jt[w * 255 + d - 1], &base);
+        for (int b = 0; b < 8; b++) p1_double(&base, &base);
+    }
+    for (int i = 0; i < 32 * 255; i++) p1_to_affine(&table[i], &jt[i]);
+    free(jt);
+    setup_fast_t *args = (setup_fast_t *)malloc(sizeof(setup_fast_t) * threads);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    for (int t = 0; t < threads; t++) {
+        args[t] = (setup_fast_t){gs, s, first, count, t, threads, table};
+        pthread_create(&th[t], NULL, setup_fast_worker, &args[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(th); free(args); free(table);
+}
+
 /* ----------------------------------------------------------------------- */
 /* G1 MSM: stands in for blstrs G1Projective::multi_exp (call sites          */
 /* coeff_form.rs:61,78,102; eval_form.rs:118,136).  Like blstrs it converts  */

@@ -1,0 +1,184 @@
+"""GPU suite, round 2: device-resident polynomial handles, the in-memory layout pinned by DOCUMENTED blst / zkcrypto
+constants (not only struct sizes), the multi-GPU C ABI (world 1 through Python; world >= 2 and host threads through the
+C++ checks of tests/cpp/), per-call device selection from foreign threads."""
+import os
+import subprocess
+import threading
+
+import numpy as np
+import pytest
+
+from kzg_b200 import scalar
+from oracle import kzg_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = O.R_MOD
+
+# ---- constants as PUBLISHED by blst (src/consts.c, e2.c) / zkcrypto bls12_381 (g1.rs, scalar.rs): raw in-memory limbs
+BLS12_381_Rx_P = [0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d,
+                  0x15f65ec3fa80e493]                                        # blst BLS12_381_Rx.p = 2^384 mod p
+BLS12_381_G1_X = [0x5cb38790fd530c16, 0x7817fc679976fff5, 0x154f95c7143ba1c1, 0xf0ae6acdf3d0e747, 0xedce6ecc21dbf440,
+                  0x120177419e0bfb75]                                        # blst BLS12_381_G1.X (Montgomery)
+BLS12_381_G1_Y = [0xbaac93d50ce72271, 0x8c22631a7918fd8e, 0xdd595f13570725ce, 0x51ac582950405194, 0x0e1c8c3fad0059c0,
+                  0x0bbc3efc5008a26a]
+FR_R = [0x00000001fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f]      # Scalar::one() = 2^256 mod r
+FR_ROOT_OF_UNITY = [0xb9b58d8c5f0e466a, 0x5b1b4c801819d7ec, 0x0af53ae352a31e64, 0x5bf3adda19e9b27b]   # Scalar::root_of_unity()
+ROOT_OF_UNITY_CANONICAL = 0x16a2a19edfe81f20d09b681922c813b4b63683508c2280b93829971f439f0d2b
+G1_X = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
+G1_Y = 0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1
+G1_COMPRESSED = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+
+
+def _limbs(v, n):
+    return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+
+
+def test_blst_memory_layout_pinned_by_published_constants(gpu):
+    """Limb ORDER and Montgomery RADIX of kzgb_fr / kzgb_fp / kzgb_p1 are asserted with the raw limb images that blst
+    and zkcrypto publish for known values -- pushed through the device as opaque blst_fr / blst_fp / blst_p1 buffers."""
+    u = lambda l: np.array(l, dtype=np.uint64).reshape(1, -1)
+    # from_mont(R) = 1, from_mont(root_of_unity limbs) = the canonical 2^32-th root of unity
+    assert gpu.test_fr_op(u(FR_R), None, 5)[0].tolist() == [1, 0, 0, 0]
+    assert gpu.test_fr_op(u(FR_ROOT_OF_UNITY), None, 5)[0].tolist() == _limbs(ROOT_OF_UNITY_CANONICAL, 4)
+    assert gpu.test_fp_op(u(BLS12_381_Rx_P), None, 5)[0].tolist() == [1, 0, 0, 0, 0, 0]
+    assert gpu.test_fp_op(u(BLS12_381_G1_X), None, 5)[0].tolist() == _limbs(G1_X, 6)
+    assert gpu.test_fp_op(u(BLS12_381_G1_Y), None, 5)[0].tolist() == _limbs(G1_Y, 6)
+    # the published root of unity has order exactly 2^32: 31 squarings give -1 = r - 1, one more gives R (= one)
+    x = u(FR_ROOT_OF_UNITY)
+    for _ in range(31):
+        x = gpu.test_fr_op(x, None, 6)
+    assert scalar.fr_int(x[0]) == R - 1
+    assert gpu.test_fr_op(x, None, 6)[0].tolist() == FR_R
+    # the published generator, as a raw blst_p1 {X, Y, Z = Rx}, times Scalar::one() through the MSM: same affine limbs,
+    # and the 48 bytes every BLS12-381 library prints for the generator
+    p1 = np.array(BLS12_381_G1_X + BLS12_381_G1_Y + BLS12_381_Rx_P, dtype=np.uint64).reshape(1, 18)
+    srs = gpu.SRS.from_jacobian(p1)
+    aff = srs.msm(u(FR_R))
+    assert aff.tolist() == BLS12_381_G1_X + BLS12_381_G1_Y
+    assert gpu.g1_compress(aff).hex() == G1_COMPRESSED
+    jac = srs.msm_jacobian(u(FR_R))          # blst_p1 out: X/Z^2 must be the published x again
+    zi = pow(O.fq_from_mont_limbs(jac[12:18]), -1, O.P_MOD)
+    assert O.fq_from_mont_limbs(jac[0:6]) * zi * zi % O.P_MOD == G1_X
+    srs.close()
+
+
+def test_device_resident_polynomial_handles(gpu, cpu):
+    """f2: commit -> create_witness -> create_witness_batched on ONE uploaded polynomial == the host-pointer calls."""
+    from kzg_b200 import KZGParams, KZGProver, Polynomial
+    from kzg_b200.params import PointNotOnPolynomial
+    n = 3000
+    s = cpu.fr_stream(69, 1)[0]
+    params = KZGParams(gpu.srs_generate(0, s, 4096))
+    prover = KZGProver(params)
+    coeffs = cpu.fr_stream(42, n)
+    host = Polynomial.new(coeffs)
+    dev = Polynomial.new(coeffs).to_device()
+    assert dev.device is not None and (dev.device.download() == coeffs).all()
+    assert (prover.commit(dev) == prover.commit(host)).all()
+    x = cpu.fr_stream(7, 1)[0]
+    y = host.eval(x)
+    assert (prover.create_witness(dev, (x, y)) == prover.create_witness(host, (x, y))).all()
+    with pytest.raises(PointNotOnPolynomial):
+        prover.create_witness(dev, (x, scalar.fr(5)))
+    xs = cpu.fr_stream(8, 9)
+    ys = np.vstack([host.eval(xi) for xi in xs])
+    a, b = prover.create_witness_batched(dev, xs, ys), prover.create_witness_batched(host, xs, ys)
+    assert a == b
+    ys[3] = scalar.fr(1)
+    with pytest.raises(PointNotOnPolynomial):
+        prover.create_witness_batched(dev, xs, ys)
+    # declared degree below the uploaded length: only coeffs[..degree+1] take part (polynomial.rs:148-154)
+    short = Polynomial(coeffs, 99).to_device()
+    assert (prover.commit(short) == prover.commit(Polynomial(coeffs[:100], 99))).all()
+    dev.release_device()
+    assert dev.device is None
+
+
+def test_device_resident_evaluation_domain(gpu, cpu):
+    from kzg_b200 import EvaluationDomain, KZGParams, KZGProverEvalForm
+    from kzg_b200.eval_form import compute_lagrange_basis_known_secret
+    d = 1 << 10
+    s = cpu.fr_stream(69, 1)[0]
+    params = KZGParams(gpu.srs_generate(0, s, d))
+    prover = KZGProverEvalForm(params, compute_lagrange_basis_known_secret(s, d))
+    evals = EvaluationDomain.from_coeffs(cpu.fr_stream(3, d))
+    ref_c, ref_w = prover.commit(evals), prover.create_witness(evals, 77)
+    evals.to_device()
+    assert evals.device is not None
+    assert (prover.commit(evals) == ref_c).all() and (prover.create_witness(evals, 77) == ref_w).all()
+    # handle-level transform == host transform; a host-side mutation drops the stale resident copy
+    h = gpu.DevicePoly(evals.coeffs)
+    h.ntt(10, False)
+    st, want = gpu.ntt(evals.coeffs, 10, False)
+    assert (h.download() == want).all()
+    h.close()
+    evals.fft()
+    assert evals.device is None and (evals.coeffs == want).all()
+
+
+def test_entry_points_from_foreign_threads(gpu, cpu):
+    """Entry points select the library's device per call: results from worker threads equal the main thread's."""
+    n = 1 << 12
+    srs = gpu.srs_generate(0, cpu.fr_stream(69, 1)[0], n)
+    p = cpu.fr_stream(42, n)
+    want_c = srs.msm(p)
+    want_f = gpu.ntt(p, 12, False)[1]
+    got = {}
+
+    def work(k):
+        got[k] = (srs.msm(p), gpu.ntt(p, 12, False)[1])
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for k in range(4):
+        assert (got[k][0] == want_c).all() and (got[k][1] == want_f).all()
+    srs.close()
+
+
+def test_sharded_entry_points_degenerate_to_single_gpu(gpu, cpu):
+    """World of one (no communicator needed): kzgb_msm_g1_sharded* and the four-step plan give the single-GPU bytes."""
+    n = 1 << 12
+    srs = gpu.srs_generate(0, cpu.fr_stream(69, 1)[0], n)
+    p, q = cpu.fr_stream(42, n), cpu.fr_stream(43, n - 7)
+    assert (gpu.msm_sharded(srs, p) == srs.msm(p)).all()
+    many = gpu.msm_sharded_batch(srs, [p, q, p[:0]])
+    assert (many[0] == srs.msm(p)).all() and (many[1] == srs.msm(q)).all() and not many[2].any()
+    for log_n in (12, 16):
+        a = cpu.fr_stream(5, 1 << log_n)
+        plan = gpu.Ntt4Plan(log_n)
+        X = plan.run_host(a, False, True)
+        assert (X == gpu.ntt(a, log_n, False)[1]).all()
+        assert (plan.run_host(X, True, False) == a).all()
+        plan.close()
+    srs.close()
+
+
+def _run(exe, *args, timeout=600):
+    path = os.path.join(ROOT, "build", exe)
+    if not os.path.exists(path):
+        pytest.skip(f"build/{exe} not built (make)")
+    return subprocess.run([path, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+
+
+def test_cpp_threads_check():
+    """4 host threads x 2 SRS handles through the C ABI (no Python in the loop): bit-equal results."""
+    r = _run("threads_check", 14, 4)
+    assert r.returncode == 0 and "threads_check: PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_multi_gpu_check(tmp_path):
+    """C++ multi-process parity of the sharded MSM and the fused four-step NTT: one process per visible GPU (2 when
+    the box has them; the world-of-one run still goes through every entry point)."""
+    import torch
+    world = 2 if torch.cuda.device_count() >= 2 else 1
+    path = os.path.join(ROOT, "build", "multi_gpu_check")
+    if not os.path.exists(path):
+        pytest.skip("build/multi_gpu_check not built (make)")
+    idf = str(tmp_path / "nccl_id")
+    procs = [subprocess.Popen([path, str(r), str(world), idf, "14", "16"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(world)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert "multi_gpu_check: PASS" in outs[0]
