@@ -170,7 +170,10 @@ KZGB_API int kzgb_witness_coeff_dev(kzgb_srs* srs, const void* d_p, size_t n, co
  * r_out receives the coefficients of r: m of them (declared degree m-1), or for m == 1 the TWO coefficients of
  * X + (y - x) -- the reference's one-point quirk (polynomial.rs:244-247).  KZGB_POINT_NOT_ON_POLYNOMIAL when the
  * remainder is non-zero (coeff_form.rs:96).  xs must be distinct (the reference panics; here KZGB_ERR_INVALID_ARG).
- * 1 <= m <= 4096. */
+ * 1 <= m <= 16384: the interpolation keeps an m x m table (32 m^2 bytes of device scratch: 512 MiB at 4096, 8 GiB at
+ * the limit), unlike the reference's SubProductTree; larger batches return KZGB_ERR_INVALID_ARG and must be split.
+ * r_out always holds exactly *r_len = m coefficients; for m >= 258 the reference's fft_mul path (polynomial.rs:167-191)
+ * returns the same coefficients in a vector zero-padded to 2^k >= m + 1 -- the host mirrors reproduce that shape. */
 KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, const kzgb_fr* xs, const kzgb_fr* ys,
                                   size_t m, kzgb_fr* r_out, size_t* r_len, kzgb_p1_affine* w_out);
 KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, const void* d_xs, const void* d_ys,
@@ -296,7 +299,11 @@ KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t
  * (blstrs to_bytes_le / from_bytes_le).  The reference's own serde support is dead code (lib.rs:13, ft.rs:389-404). */
 KZGB_API int kzgb_g1_compress(const kzgb_p1_affine* points, size_t n, uint8_t* out48);
 KZGB_API int kzgb_g1_decompress(const uint8_t* in48, size_t n, kzgb_p1_affine* out);
+/* SRS import is checked like blstrs `from_compressed` (well-formed, on the curve, in the prime-order subgroup: [r]P = O,
+ * ~0.13 s per 2^20 points, once); the _unchecked variant skips the subgroup test for pre-validated input. */
 KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out);
+KZGB_API int kzgb_srs_create_g1_compressed_unchecked(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out);
+KZGB_API int kzgb_g1_subgroup_check(const kzgb_p1_affine* points, size_t n, int* all_in_g1);
 KZGB_API int kzgb_srs_export_compressed(const kzgb_srs* srs, size_t start, size_t count, uint8_t* out48);
 KZGB_API int kzgb_fr_bytes_le(const void* in, void* out, size_t n, int to_bytes);
 

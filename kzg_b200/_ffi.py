@@ -483,12 +483,22 @@ def g1_decompress(data: bytes) -> np.ndarray:
     return out
 
 
-def srs_from_compressed(data: bytes, window_bits: int = 0) -> SRS:
+def srs_from_compressed(data: bytes, window_bits: int = 0, subgroup_check: bool = True) -> SRS:
+    """SRS from 48-byte compressed points; checked like blstrs `from_compressed` (subgroup included) unless
+    subgroup_check=False (`from_compressed_unchecked`)."""
     buf = np.frombuffer(data, dtype=np.uint8).copy()
     assert len(buf) % 48 == 0
     h = C.c_void_p()
-    check(lib().kzgb_srs_create_g1_compressed(ptr(buf), C.c_size_t(len(buf) // 48), C.c_int(window_bits), C.byref(h)))
+    fn = lib().kzgb_srs_create_g1_compressed if subgroup_check else lib().kzgb_srs_create_g1_compressed_unchecked
+    check(fn(ptr(buf), C.c_size_t(len(buf) // 48), C.c_int(window_bits), C.byref(h)))
     return SRS(h)
+
+
+def g1_subgroup_check(points) -> bool:
+    pts = u64(points, (-1, 12))
+    ok = C.c_int(0)
+    check(lib().kzgb_g1_subgroup_check(ptr(pts), C.c_size_t(len(pts)), C.byref(ok)))
+    return bool(ok.value)
 
 
 def srs_export_compressed(srs: SRS, start: int = 0, count=None) -> bytes:

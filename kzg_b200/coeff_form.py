@@ -92,7 +92,7 @@ class KZGProver:
             st, r, w = _ffi.witness_batched(self._parameters.srs, polynomial.slice_coeffs(), xs, ys)
         if st == _ffi.KZGB_POINT_NOT_ON_POLYNOMIAL:
             raise PointNotOnPolynomial()
-        return KZGBatchWitness(Polynomial(r, len(r) - 1), w)
+        return KZGBatchWitness(Polynomial.from_interpolant(r, len(xs)), w)
 
 
 class KZGVerifier:

@@ -41,7 +41,7 @@ KZG_DI void b_st(Fr* p, const Fr& v) {
 }
 
 // ---- K11: interpolation ------------------------------------------------------
-// These kernels work on m <= 4096 values: a handful of warps each, so their cost is the LENGTH OF THE DEPENDENT CHAIN
+// These kernels work on m <= 16384 (typically a few hundred) values: a handful of warps each, so their cost is the LENGTH OF THE DEPENDENT CHAIN
 // per thread (a dependent Fr product costs ~0.3-0.6 us), not arithmetic.  Every output is therefore computed by a
 // group of IL = 8 adjacent lanes that split the chain and combine with shuffles (field sums and products are exact,
 // so the grouping does not change a single bit of the result).
@@ -277,14 +277,18 @@ __global__ void diff_nonzero_kernel(const Fr* __restrict__ a, size_t na, const F
 
 // ---- host drivers --------------------------------------------------------------
 static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+// Number of opening points of one batched witness.  The power-sum table of the interpolation is m x m field elements
+// (32 m^2 bytes of scratch: 512 MiB at m = 4096, 8 GiB at the limit); the reference's SubProductTree has no such
+// limit (coeff_form.rs:83-111), so larger batches must be split by the caller.
+constexpr size_t KZG_MAX_BATCH_POINTS = 16384;
 
 size_t interp_workspace_bytes(size_t m) { return al((m * m + 6 * (m + 1)) * sizeof(Fr)) + 256; }
 
 // d_r receives max(m,2) coefficients (m == 1: the two coefficients of X + (y - x)); d_Z receives m+1.
 int interpolate_run(const Fr* d_xs, const Fr* d_ys, size_t m, Fr* d_r, Fr* d_Z, int* d_flag, void* d_ws,
                     cudaStream_t stream) {
-    if (m == 0 || m > 4096) {
-        set_error("interpolate: number of points %zu out of range (1 .. 4096)", m);
+    if (m == 0 || m > KZG_MAX_BATCH_POINTS) {
+        set_error("interpolate: number of points %zu out of range (1 .. %zu)", m, KZG_MAX_BATCH_POINTS);
         return KZGB_ERR_INVALID_ARG;
     }
     StageScope sc(ST_INTERP, stream);
@@ -389,8 +393,8 @@ KZGB_API int kzgb_interpolate(const kzgb_fr* xs, const kzgb_fr* ys, size_t m, kz
     Context& c = ctx();
     (void)c;
     use_stream(lane().stream);
-    if (!xs || !ys || !r_out || !r_len || m == 0 || m > 4096) {
-        set_error("kzgb_interpolate: bad argument (1 <= m <= 4096)");
+    if (!xs || !ys || !r_out || !r_len || m == 0 || m > KZG_MAX_BATCH_POINTS) {
+        set_error("kzgb_interpolate: bad argument (1 <= m <= 16384; the workspace is 32 m^2 bytes)");
         return KZGB_ERR_INVALID_ARG;
     }
     size_t mb = al(m * 32), rb = al((m + 2) * 32);
@@ -425,8 +429,8 @@ KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, 
     KZG_ENTER();
     Context& c = ctx();
     (void)c;
-    if (!srs || !d_p || !d_xs || !d_ys || !d_r_out || !d_out || n == 0 || m == 0 || m > 4096) {
-        set_error("kzgb_witness_batched_dev: bad argument (1 <= m <= 4096)");
+    if (!srs || !d_p || !d_xs || !d_ys || !d_r_out || !d_out || n == 0 || m == 0 || m > KZG_MAX_BATCH_POINTS) {
+        set_error("kzgb_witness_batched_dev: bad argument (1 <= m <= 16384; the workspace is 32 m^2 bytes)");
         return KZGB_ERR_INVALID_ARG;
     }
     KZG_LOCK_SRS(srs);
@@ -471,8 +475,8 @@ KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, con
     Context& c = ctx();
     (void)c;
     use_stream(lane().stream);
-    if (!srs || !p || !xs || !ys || !r_out || !r_len || !w_out || n == 0 || m == 0 || m > 4096) {
-        set_error("kzgb_witness_batched: bad argument (1 <= m <= 4096)");
+    if (!srs || !p || !xs || !ys || !r_out || !r_len || !w_out || n == 0 || m == 0 || m > KZG_MAX_BATCH_POINTS) {
+        set_error("kzgb_witness_batched: bad argument (1 <= m <= 16384; the workspace is 32 m^2 bytes)");
         return KZGB_ERR_INVALID_ARG;
     }
     KZG_LOCK_SRS(srs);

@@ -85,6 +85,24 @@ __global__ void __launch_bounds__(128) g1_decompress_kernel(const uint8_t* __res
     stg_affine(&out[i], Affine{x, y});
 }
 
+// Prime-order subgroup membership: [r]P == O (r = the scalar-field modulus).  E(Fq) has order h*r with cofactor
+// h = 0x396c8c005555e1568c00aaab0000aaab, so an on-curve point from an untrusted file need not lie in G1; blstrs'
+// `from_compressed` performs this check, `from_compressed_unchecked` does not.  Plain double-and-add over the 255 bits
+// of r: one-off import cost (~0.13 s per 2^20 points), never on the prover path.
+__global__ void __launch_bounds__(128) g1_subgroup_check_kernel(const Affine* __restrict__ pts, size_t n, int* __restrict__ bad) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine p = ldg_affine(&pts[i]);
+    if (p.is_inf()) return;
+    XYZZ acc = XYZZ::inf();
+#pragma unroll 1
+    for (int k = 254; k >= 0; k--) {
+        acc = xyzz_dbl(acc);
+        if ((Fr::mod_limb(k >> 5) >> (k & 31)) & 1) xyzz_madd(acc, p.x, p.y);
+    }
+    if (!acc.is_inf()) atomicMax(bad, 3);
+}
+
 // canonical little-endian bytes <-> Montgomery limbs
 __global__ void fr_bytes_kernel(const Fr* __restrict__ in, Fr* __restrict__ out, size_t n, int to_bytes, int* __restrict__ bad) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -150,7 +168,7 @@ KZGB_API int kzgb_srs_export_compressed(const kzgb_srs* s, size_t start, size_t 
     return KZGB_OK;
 }
 
-static int decompress_to(const uint8_t* in48, size_t n, Affine* d_out, cudaStream_t stream) {
+static int decompress_to(const uint8_t* in48, size_t n, Affine* d_out, cudaStream_t stream, bool subgroup_check = false) {
     Context& c = ctx();
     char* d = (char*)staging_reserve(al_w(n * 48) + 256);
     if (!d) return KZGB_ERR_CUDA;
@@ -159,12 +177,18 @@ static int decompress_to(const uint8_t* in48, size_t n, Affine* d_out, cudaStrea
     KZG_CUDA(cudaMemsetAsync(d_bad, 0, 4, stream));
     g1_decompress_kernel<<<div_up(n, 128), 128, 0, stream>>>((const uint8_t*)d, n, d_out, d_bad);
     KZG_LAUNCHED();
+    if (subgroup_check) {
+        g1_subgroup_check_kernel<<<div_up(n, 128), 128, 0, stream>>>(d_out, n, d_bad);
+        KZG_LAUNCHED();
+    }
     int bad = 0;
     KZG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, stream));
     KZG_CUDA(cudaStreamSynchronize(stream));
     (void)c;
     if (bad) {
-        set_error(bad == 1 ? "g1 decompress: malformed encoding (flags, or x >= p)" : "g1 decompress: x is not on the curve");
+        set_error(bad == 1 ? "g1 decompress: malformed encoding (flags, or x >= p)"
+                  : (bad == 2 ? "g1 decompress: x is not on the curve"
+                              : "g1 decompress: a point is on the curve but not in the prime-order subgroup G1"));
         return KZGB_ERR_INVALID_ARG;
     }
     return KZGB_OK;
@@ -188,8 +212,32 @@ KZGB_API int kzgb_g1_decompress(const uint8_t* in48, size_t n, kzgb_p1_affine* o
     return KZGB_OK;
 }
 
-// SRS handle straight from a compressed-point file image
-KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out) {
+// n affine points (host) -> *all_in_g1 = 1 iff every point is the identity or lies in the prime-order subgroup
+KZGB_API int kzgb_g1_subgroup_check(const kzgb_p1_affine* points, size_t n, int* all_in_g1) {
+    KZG_REQUIRE_INIT();
+    KZG_ENTER();
+    use_stream(lane().stream);
+    if ((!points && n) || !all_in_g1) { set_error("kzgb_g1_subgroup_check: null argument"); return KZGB_ERR_INVALID_ARG; }
+    *all_in_g1 = 1;
+    if (n == 0) return KZGB_OK;
+    char* d = (char*)staging_reserve(al_w(n * sizeof(Affine)) + 256);
+    if (!d) return KZGB_ERR_CUDA;
+    int* d_bad = (int*)(d + al_w(n * sizeof(Affine)));
+    KZG_CUDA(cudaMemcpyAsync(d, points, n * sizeof(Affine), cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(cudaMemsetAsync(d_bad, 0, 4, lane().stream));
+    g1_subgroup_check_kernel<<<div_up(n, 128), 128, 0, lane().stream>>>((const Affine*)d, n, d_bad);
+    KZG_LAUNCHED();
+    int bad = 0;
+    KZG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(cudaStreamSynchronize(lane().stream));
+    *all_in_g1 = bad ? 0 : 1;
+    return KZGB_OK;
+}
+
+// SRS handle straight from a compressed-point file image.  Checked like blstrs `from_compressed`: well-formed, on the
+// curve AND in the prime-order subgroup; the _unchecked variant skips the subgroup test (`from_compressed_unchecked`)
+// for inputs that were validated elsewhere.
+static int srs_from_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out, bool subgroup_check) {
     KZG_REQUIRE_INIT();
     KZG_ENTER();
     Context& c = ctx();
@@ -199,7 +247,7 @@ KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int wi
     kzgb_srs* h = nullptr;
     int st = srs_alloc(&h, n, window_bits);
     if (st) return st;
-    st = decompress_to(in48, n, h->table, lane().stream);
+    st = decompress_to(in48, n, h->table, lane().stream, subgroup_check);
     if (!st) st = srs_build_table(h, lane().stream);
     if (!st) {
         cudaError_t e = cudaStreamSynchronize(lane().stream);
@@ -208,6 +256,12 @@ KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int wi
     if (st) { srs_free(h); return st; }
     *out = h;
     return KZGB_OK;
+}
+KZGB_API int kzgb_srs_create_g1_compressed(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out) {
+    return srs_from_compressed(in48, n, window_bits, out, true);
+}
+KZGB_API int kzgb_srs_create_g1_compressed_unchecked(const uint8_t* in48, size_t n, int window_bits, kzgb_srs** out) {
+    return srs_from_compressed(in48, n, window_bits, out, false);
 }
 
 // Fr vectors: Montgomery limbs -> canonical little-endian 32-byte strings (to_bytes = 1) or back (to_bytes = 0;

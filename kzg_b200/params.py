@@ -48,9 +48,11 @@ class KZGParams:
         return cls(_ffi.SRS.from_affine(gs, window_bits))
 
     @classmethod
-    def from_compressed(cls, data: bytes, window_bits: int = 0) -> "KZGParams":
-        """G1 powers from a ceremony-style file image: n x 48-byte compressed points (decompressed on the device)."""
-        return cls(_ffi.srs_from_compressed(data, window_bits))
+    def from_compressed(cls, data: bytes, window_bits: int = 0, subgroup_check: bool = True) -> "KZGParams":
+        """G1 powers from a ceremony-style file image: n x 48-byte compressed points (decompressed on the device).
+        Checked like blstrs `from_compressed` -- encoding, on-curve and prime-order subgroup; pass
+        subgroup_check=False (`from_compressed_unchecked`) only for input validated elsewhere."""
+        return cls(_ffi.srs_from_compressed(data, window_bits, subgroup_check))
 
     def to_compressed(self) -> bytes:
         return _ffi.srs_export_compressed(self._srs)

@@ -138,8 +138,26 @@ class Polynomial:
         return self.fft_mul(other)
 
     @staticmethod
+    def from_interpolant(r, m: int) -> "Polynomial":
+        """Wraps the m interpolant coefficients the device returns in the SHAPE the reference's tree recursion gives
+        them (polynomial.rs:303-365): the top-level `right.product.best_mul(&l) + left.product.best_mul(&r)` takes the
+        fft_mul path once both operands have degree >= 128 (polynomial.rs:185-191), i.e. for m >= 258, and fft_mul
+        returns the full padded transform length with a re-measured degree (polynomial.rs:167-183, Polynomial::new);
+        `Add` keeps the longer operand's vector.  Below the threshold: exactly m coefficients, declared degree m - 1."""
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+        if m >= 258:
+            size = 1
+            while size < m + 1:
+                size *= 2
+            padded = np.zeros((size, 4), dtype=np.uint64)
+            padded[: len(r)] = r
+            # re-measured (Polynomial::new): generically m - 1; lower only if the top coefficients really vanish
+            return Polynomial(padded, Polynomial.compute_degree(padded, len(r) - 1))
+        return Polynomial(r, len(r) - 1)
+
+    @staticmethod
     def lagrange_interpolation(xs, ys) -> "Polynomial":
         """polynomial.rs:237-293.  One point gives X + (y - x) (degree 1) exactly as the reference does
-        (:244-247); m >= 2 points give m coefficients with declared degree m - 1."""
+        (:244-247); m >= 2 points give m coefficients with declared degree m - 1 (m >= 258: see from_interpolant)."""
         r = _ffi.interpolate(xs, ys)
-        return Polynomial(r, len(r) - 1)
+        return Polynomial.from_interpolant(r, len(_ffi.u64(xs, (-1, 4))))

@@ -182,3 +182,64 @@ def test_cpp_multi_gpu_check(tmp_path):
     outs = [p.communicate(timeout=600)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert "multi_gpu_check: PASS" in outs[0]
+
+
+def test_srs_import_rejects_points_outside_the_subgroup(gpu, cpu):
+    """blstrs `from_compressed` semantics on the SRS import path: a point ON the curve but OUTSIDE G1 is refused
+    (the cofactor of E(Fq) is ~2^126, so almost every curve point is such a point); the unchecked variant takes it."""
+    P = O.P_MOD
+    x = 1
+    while True:       # first small x with x^3 + 4 a square: that curve point is not in G1 (checked below by [r]P != O)
+        rhs = (x ** 3 + 4) % P
+        y = pow(rhs, (P + 1) // 4, P)
+        if y * y % P == rhs:
+            break
+        x += 1
+    enc = bytearray(x.to_bytes(48, "big"))
+    enc[0] |= 0x80 | (0x20 if y > (P - 1) // 2 else 0)
+    good = gpu.srs_export_compressed(gpu.srs_generate(0, cpu.fr_stream(69, 1)[0], 4))
+    blob = good[:96] + bytes(enc) + good[96:]
+    with pytest.raises(gpu.KZGBackendError, match="subgroup"):
+        gpu.srs_from_compressed(blob)
+    srs = gpu.srs_from_compressed(blob, subgroup_check=False)
+    pts = srs.read_affine()
+    assert O.fq_from_mont_limbs(pts[2][:6]) == x
+    assert gpu.g1_subgroup_check(pts[:2]) and gpu.g1_subgroup_check(pts[3:]) and not gpu.g1_subgroup_check(pts)
+    assert gpu.srs_from_compressed(good) is not None            # honest input still loads
+
+
+def test_interpolant_shape_follows_the_reference_at_the_fft_mul_threshold(gpu, cpu):
+    """m >= 258: the reference's top-level best_mul takes the fft_mul path (polynomial.rs:167-191) and r comes back in a
+    vector padded to 2^k >= m + 1 with a re-measured degree; below, exactly m coefficients (oracle: tree recursion)."""
+    from kzg_b200 import Polynomial
+    for m in (257, 258, 300):
+        xs, ys = cpu.fr_stream(21, m), cpu.fr_stream(22, m)
+        r = Polynomial.lagrange_interpolation(xs, ys)
+        tree = O.SubProductTree.new_from_points(scalar.fr_vec_int(xs))
+        ref = O.Polynomial.lagrange_interpolation_with_tree(scalar.fr_vec_int(xs), scalar.fr_vec_int(ys), tree)
+        assert (r.degree, len(r.coeffs)) == (ref.degree, len(ref.coeffs))
+        assert scalar.fr_vec_int(r.coeffs) == [c % R for c in ref.coeffs]
+
+
+def test_batched_witness_beyond_4096_points(gpu, cpu):
+    """The round-1 cap (m <= 4096) is lifted to 16384: m = 4500 openings of a degree-5999 polynomial, checked through
+    the closed form under the known secret, w = ((p(s) - r(s)) / Z(s)) * G, and r(x_i) = y_i on a sample."""
+    n, m = 6000, 4500
+    s = cpu.fr_stream(69, 1)[0]
+    srs = gpu.srs_generate(0, s, n)
+    p = cpu.fr_stream(42, n)
+    xs = cpu.fr_stream(7, m)
+    ys = np.vstack([cpu.poly_eval(p, x) for x in xs])
+    st, r, w = gpu.witness_batched(srs, p, xs, ys)
+    assert st == 0 and len(r) == m
+    for i in (0, 1, m // 2, m - 1):
+        assert (cpu.poly_eval(r, xs[i]) == ys[i]).all()
+    si = scalar.fr_int(s)
+    zs = 1
+    for x in scalar.fr_vec_int(xs):
+        zs = zs * (si - x) % R
+    k = (scalar.fr_int(cpu.poly_eval(p, s)) - scalar.fr_int(cpu.poly_eval(r, s))) * pow(zs, -1, R) % R
+    assert (w == cpu.g1_to_affine(cpu.g1_mul(cpu.g1_generator(), scalar.fr(k)))[0]).all()
+    ys[17] = scalar.fr(3)
+    assert gpu.witness_batched(srs, p, xs, ys)[0] == gpu.KZGB_POINT_NOT_ON_POLYNOMIAL
+    srs.close()
