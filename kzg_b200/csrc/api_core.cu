@@ -76,6 +76,19 @@ cudaStream_t use_stream(cudaStream_t s) {
     return s;
 }
 
+int lane_side_stream(cudaStream_t* side, cudaEvent_t* fork_ev, cudaEvent_t* join_ev) {
+    Lane& l = lane();
+    if (!l.side) {
+        KZG_CUDA(cudaStreamCreateWithFlags(&l.side, cudaStreamNonBlocking));
+        KZG_CUDA(cudaEventCreateWithFlags(&l.fork_ev, cudaEventDisableTiming));
+        KZG_CUDA(cudaEventCreateWithFlags(&l.join_ev, cudaEventDisableTiming));
+    }
+    *side = l.side;
+    *fork_ev = l.fork_ev;
+    *join_ev = l.join_ev;
+    return KZGB_OK;
+}
+
 // Arena growth frees the old block: everything that may still be reading it (the lane's last stream) is drained first.
 static void lane_drain(Lane& l) {
     if (l.have_last) cudaStreamSynchronize(l.last_stream);
@@ -301,6 +314,7 @@ int kzgb_shutdown(void) {
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
     comm_shutdown();
+    poly_cache_shutdown();
     {   // live SRS handles: release their device memory now; kzgb_srs_destroy then only frees the host struct
         std::lock_guard<std::mutex> g(g_srs_mu);
         for (kzgb_srs* s : g_live_srs) srs_release_device(s);
@@ -320,6 +334,9 @@ int kzgb_shutdown(void) {
         if (l.staging) cudaFree(l.staging);
         if (l.pinned) cudaFreeHost(l.pinned);
         if (l.stream) cudaStreamDestroy(l.stream);
+        if (l.side) cudaStreamDestroy(l.side);
+        if (l.fork_ev) cudaEventDestroy(l.fork_ev);
+        if (l.join_ev) cudaEventDestroy(l.join_ev);
         l = Lane();
     }
     c.initialised = false;

@@ -7,6 +7,7 @@
 // the point (x, y) in and 96 bytes out.
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "ec.cuh"
@@ -17,15 +18,61 @@ struct kzgb_poly {
     size_t n = 0;
     kzg::Fr* d_data = nullptr;
     kzg::Fr* d_work = nullptr;   // n + 1 elements of quotient scratch, allocated on first witness
+    size_t data_cap = 0, work_cap = 0;
     std::recursive_mutex mu;
 };
 
 using namespace kzg;
 
+// Handles come and go with the caller's polynomials; cudaMalloc / cudaFree cost anything from 10 us to 100 ms on a busy
+// box (measured: a commit + 8 witnesses sequence took 65 or 184 ms depending on them), so released buffers are parked
+// in a small cache and handed to the next handle that fits.
+namespace {
+struct Parked { void* p; size_t bytes; };
+std::mutex g_cache_mu;
+std::vector<Parked> g_cache;
+constexpr size_t POLY_CACHE_ENTRIES = 8;
+
+cudaError_t poly_alloc(void** out, size_t bytes, size_t* capacity) {
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i].bytes >= bytes && g_cache[i].bytes <= 2 * bytes + 4096 && (best < 0 || g_cache[i].bytes < g_cache[best].bytes))
+                best = (int)i;
+        if (best >= 0) {
+            *out = g_cache[best].p;
+            *capacity = g_cache[best].bytes;
+            g_cache[best] = g_cache.back();
+            g_cache.pop_back();
+            return cudaSuccess;
+        }
+    }
+    *capacity = bytes;
+    return cudaMalloc(out, bytes);
+}
+void poly_release(void* p, size_t capacity) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        if (g_cache.size() < POLY_CACHE_ENTRIES) { g_cache.push_back(Parked{p, capacity}); return; }
+    }
+    cudaFree(p);
+}
+}  // namespace
+
+namespace kzg {
+void poly_cache_shutdown() {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    for (auto& e : g_cache) cudaFree(e.p);
+    g_cache.clear();
+}
+}  // namespace kzg
+
 #define KZG_LOCK_POLY(p) std::lock_guard<std::recursive_mutex> _poly_guard((p)->mu)
 
 static int poly_work(kzgb_poly* p) {
-    if (!p->d_work) KZG_CUDA(cudaMalloc((void**)&p->d_work, (p->n + 1) * sizeof(Fr)));
+    if (!p->d_work) KZG_CUDA(poly_alloc((void**)&p->d_work, (p->n + 1) * sizeof(Fr), &p->work_cap));
     return KZGB_OK;
 }
 
@@ -37,7 +84,7 @@ KZGB_API int kzgb_poly_upload(const kzgb_fr* coeffs, size_t n, kzgb_poly** out) 
     if (!coeffs || !out || n == 0) { set_error("kzgb_poly_upload: bad argument"); return KZGB_ERR_INVALID_ARG; }
     kzgb_poly* p = new kzgb_poly();
     p->n = n;
-    cudaError_t e = cudaMalloc((void**)&p->d_data, n * sizeof(Fr));
+    cudaError_t e = poly_alloc((void**)&p->d_data, n * sizeof(Fr), &p->data_cap);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_data, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, lane().stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(lane().stream);
     if (e != cudaSuccess) {
@@ -53,9 +100,10 @@ KZGB_API int kzgb_poly_free(kzgb_poly* p) {
     if (!p) return KZGB_OK;
     if (ctx().initialised) {   // after kzgb_shutdown the context's memory is gone with the device reset of the caller
         KZG_ENTER();
-        { KZG_LOCK_POLY(p); cudaDeviceSynchronize(); }
-        if (p->d_data) cudaFree(p->d_data);
-        if (p->d_work) cudaFree(p->d_work);
+        // every entry point that uses the handle drains its stream before returning, so nothing is in flight on it
+        { KZG_LOCK_POLY(p); }
+        poly_release(p->d_data, p->data_cap);
+        poly_release(p->d_work, p->work_cap);
     }
     delete p;
     return KZGB_OK;

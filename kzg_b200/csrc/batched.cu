@@ -221,6 +221,20 @@ __global__ void coset_scale_kernel(const Fr* __restrict__ a, size_t na, const Fr
     }
 }
 
+// dst[j] -= r[j] * s^j for j < lr (the interpolant's share of the numerator, applied after the p-only scaling)
+__global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restrict__ r, size_t lr, const Fr* __restrict__ shift) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * CS_CHUNK;
+    if (lo >= lr) return;
+    size_t hi = min(lo + CS_CHUNK, lr);
+    const Fr s = shift[0];
+    Fr pw = s.pow_u64(lo);
+    for (size_t j = lo; j < hi; j++) {
+        b_st(&dst[j], b_ld(&dst[j]) - b_ld(&r[j]) * pw);
+        pw = pw * s;
+    }
+}
+
 constexpr int PD_BATCH = 32;
 // a[j] <- a[j] / z[j], inversions batched per thread
 __global__ void __launch_bounds__(128) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N) {
@@ -334,11 +348,14 @@ size_t batch_div_workspace_bytes(size_t n, size_t m) {
 
 // psi = (p - r) div Z.  d_p: n coefficients; d_r: lr coefficients; d_Z: m+1 coefficients (monic).
 // d_psi receives *psi_len coefficients.  d_flag |= 1 when Z does not divide p - r.
+// r_ready != nullptr: d_r and d_Z are being produced on another stream and are complete once r_ready has fired; the
+// work that needs neither (the coset shift and the scaling of p, half of this function's memory traffic) is issued first.
 int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr* d_Z, const Fr* d_xs, size_t m,
-                     Fr* d_psi, size_t* psi_len, int* d_flag, void* d_ws, cudaStream_t stream) {
+                     Fr* d_psi, size_t* psi_len, int* d_flag, void* d_ws, cudaStream_t stream, cudaEvent_t r_ready) {
     StageScope sc(ST_BATCH_DIV, stream);
     size_t L = n > lr ? n : lr;  // numerator length (Sub for &Polynomial, polynomial.rs:443-460)
     if (L <= m) {
+        if (r_ready) KZG_CUDA(cudaStreamWaitEvent(stream, r_ready, 0));
         // deg(numerator) < deg Z: quotient is the zero polynomial; fine only if the numerator is zero
         // (polynomial.rs:194-199)
         diff_nonzero_kernel<<<div_up(L, 256), 256, 0, stream>>>(d_p, n, d_r, lr, L, d_flag);
@@ -360,13 +377,21 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
     coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, shift);
     KZG_LAUNCHED();
     unsigned gsz = div_up((N + CS_CHUNK - 1) / CS_CHUNK, 128);
-    coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, A);
-    KZG_LAUNCHED();
+    if (r_ready) {
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, nullptr, 0, L, N, shift, A);      // p * s^j alone
+        KZG_LAUNCHED();
+        KZG_CUDA(cudaStreamWaitEvent(stream, r_ready, 0));
+        coset_sub_scaled_kernel<<<div_up((lr + CS_CHUNK - 1) / CS_CHUNK, 128), 128, 0, stream>>>(A, d_r, lr, shift);
+        KZG_LAUNCHED();
+    } else {
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, A);
+        KZG_LAUNCHED();
+    }
     coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, Zb);
     KZG_LAUNCHED();
     int st = ntt_run(A, tmp, log_n, false, stream);
     if (st) return st;
-    st = ntt_run(Zb, tmp, log_n, false, stream);
+    st = ntt_run(Zb, tmp, log_n, false, stream, 1, nullptr, (uint32_t)(m + 1));   // Z has m + 1 coefficients
     if (st) return st;
     pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, 128), 128, 0, stream>>>(A, Zb, N);
     KZG_LAUNCHED();
@@ -438,20 +463,30 @@ KZGB_API int kzgb_witness_batched_dev(kzgb_srs* srs, const void* d_p, size_t n, 
     size_t lr = m == 1 ? 2 : m;
     size_t L = n > lr ? n : lr;
     size_t zb = al((m + 2) * 32), psib = al((L + 1) * 32);
-    size_t wsb = std::max(interp_workspace_bytes(m), batch_div_workspace_bytes(n, m));
-    char* d = (char*)scratch_reserve(zb + psib + 256 + wsb);
+    // The interpolation (a handful of small, latency-bound kernels) runs on the lane's side stream BESIDE the coset
+    // shift and the scaling of p, which need neither r nor Z: two workspaces instead of one shared one.
+    const size_t iws = al(interp_workspace_bytes(m)), dws = batch_div_workspace_bytes(n, m);
+    char* d = (char*)scratch_reserve(zb + psib + 256 + iws + dws);
     if (!d) return KZGB_ERR_CUDA;
     Fr* d_Z = (Fr*)d;
     Fr* d_psi = (Fr*)(d + zb);
     int* d_flag = (int*)(d + zb + psib);
-    char* ws = d + zb + psib + 256;
+    char* ws_i = d + zb + psib + 256;
+    char* ws_d = ws_i + iws;
+    cudaStream_t side;
+    cudaEvent_t fork_ev, join_ev;
+    int rc = lane_side_stream(&side, &fork_ev, &join_ev);
+    if (rc) return rc;
     KZG_CUDA(cudaMemsetAsync(d_flag, 0, 4, st));
-    int rc = interpolate_run((const Fr*)d_xs, (const Fr*)d_ys, m, (Fr*)d_r_out, d_Z, d_flag, ws, st);
-    if (rc) return rc;
+    KZG_CUDA(cudaEventRecord(fork_ev, st));
+    KZG_CUDA(cudaStreamWaitEvent(side, fork_ev, 0));
+    rc = interpolate_run((const Fr*)d_xs, (const Fr*)d_ys, m, (Fr*)d_r_out, d_Z, d_flag, ws_i, side);
+    if (rc) { cudaStreamSynchronize(side); return rc; }
+    KZG_CUDA(cudaEventRecord(join_ev, side));
     size_t psi_len = 0;
-    rc = batch_divide_run((const Fr*)d_p, n, (const Fr*)d_r_out, lr, d_Z, (const Fr*)d_xs, m, d_psi, &psi_len, d_flag, ws,
-                          st);
-    if (rc) return rc;
+    rc = batch_divide_run((const Fr*)d_p, n, (const Fr*)d_r_out, lr, d_Z, (const Fr*)d_xs, m, d_psi, &psi_len, d_flag, ws_d,
+                          st, join_ev);
+    if (rc) { cudaStreamSynchronize(side); return rc; }
     if (psi_len > srs->n) {
         set_error("kzgb_witness_batched: quotient has %zu coefficients but the SRS holds %zu points", psi_len, srs->n);
         return KZGB_ERR_INVALID_ARG;

@@ -27,6 +27,9 @@ struct Lane {
     size_t scratch_bytes = 0;
     void* staging = nullptr;  // device copies of host-pointer inputs (outer level; scratch is the inner level)
     size_t staging_bytes = 0;
+    // fork/join inside one call (independent sub-chains of a pipeline run beside each other, see batched.cu)
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 constexpr int KZG_MAX_LANES = 4;
 
@@ -65,6 +68,7 @@ struct ApiScope {
 // Every entry point runs its work on ONE stream.  A lane's arenas (and an SRS handle's work areas, see msm.cuh) are
 // reused between calls, so when consecutive users run on different streams the earlier stream is drained first.
 cudaStream_t use_stream(cudaStream_t s);
+int lane_side_stream(cudaStream_t* side, cudaEvent_t* fork_ev, cudaEvent_t* join_ev);   // created on first use
 void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
 void* staging_reserve(size_t bytes);   // device staging for host-pointer entry points
 void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr (error set)

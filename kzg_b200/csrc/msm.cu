@@ -303,14 +303,17 @@ KZG_DI XYZZ block_tree_sum_coop(XYZZ v, XYZZ* sh /* NT/4 entries */) {
 // the natural run pairs are (2a+1, 2a+2): ranges start at odd slots ([0, F+1), [F+1, 2F+1), ...) to keep such pairs
 // inside one thread.  A bounded look-ahead past the range end decides whether the last run is finished; if it cannot
 // tell, the run is forwarded to the next level.
-constexpr uint32_t FIX_F = 16;
+constexpr uint32_t FIX_F = 16;        // slots per thread from level 1 on
+constexpr uint32_t FIX_F_MIN = 4;     // level 0: slots per thread are chosen per launch (see msm_run), in [4, 30]
+constexpr uint32_t FIX_F_MAX = 30;
 constexpr uint32_t FIX_PEEK = 4;
 
 template <bool COOP>
 __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
                                                               const PartialMeta* __restrict__ min_, uint32_t nslots_in,
                                                               XYZZ* __restrict__ buckets, XYZZ* __restrict__ pout,
-                                                              PartialMeta* __restrict__ mout, uint32_t nthreads) {
+                                                              PartialMeta* __restrict__ mout, uint32_t nthreads,
+                                                              uint32_t F) {
     // COOP: one 4-lane group per range (the four lanes run the same control flow on the same data, lane 0 stores) --
     // used from level 1 on, where partials are sparse and latency is all that matters; level 0 is dense and uses
     // one thread per range.
@@ -318,13 +321,13 @@ __global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __rest
     const uint32_t t = COOP ? gt >> 2 : gt;
     const bool lead = COOP ? (threadIdx.x & 3) == 0 : true;
     if (t >= nthreads) return;
-    uint32_t lo = t ? t * FIX_F + 1 : 0;
-    uint32_t hi = min((t + 1) * FIX_F + 1, nslots_in);
+    uint32_t lo = t ? t * F + 1 : 0;
+    uint32_t hi = min((t + 1) * F + 1, nslots_in);
     PartialMeta m0{SLOT_EMPTY, 0}, m1{SLOT_EMPTY, 0};
     XYZZ acc = XYZZ::inf();
     uint32_t cur = SLOT_EMPTY, cur_start = 0;
     bool flushed_any = false;
-    // valid slots of the range as a bit mask (FIX_F + 1 <= 32 slots); lanes then walk their k-th valid slot
+    // valid slots of the range as a bit mask (F + 1 <= 32 slots); lanes then walk their k-th valid slot
     // together, so sparse levels pay one point addition per round instead of one per slot position
     uint32_t mask = 0;
     for (uint32_t j = lo; j < hi; j++)
@@ -545,17 +548,22 @@ __global__ void msm_finish_kernel(const XYZZ* __restrict__ in, void* __restrict_
     }
 }
 
-// sum of `count` XYZZ/Jacobian partial results (multi-GPU combine) -> finish
-__global__ void msm_combine_kernel(const XYZZ* __restrict__ in, uint32_t count, XYZZ* __restrict__ out,
-                                   uint32_t rank_stride) {
-    if (threadIdx.x) return;
-    // block b sums in[g * rank_stride + b], g < count (one block per item of a batch; a single item has stride 1)
+// sum of `count` XYZZ partial results (multi-GPU combine): block b sums in[g * rank_stride + b], g < count (one block
+// per item of a batch; a single item has stride 1).  One 4-lane group per partial, cooperative tree sum: log2(count)
+// cooperative additions (~7 us each) instead of count - 1 single-thread ones (~10 us each) on the critical path of
+// every sharded commit.
+constexpr int COMBINE_THREADS = 64;   // 16 groups = NTT_MAX_PEERS ranks in one round
+__global__ void __launch_bounds__(COMBINE_THREADS) msm_combine_kernel(const XYZZ* __restrict__ in, uint32_t count,
+                                                                      XYZZ* __restrict__ out, uint32_t rank_stride) {
+    __shared__ XYZZ sh[COMBINE_THREADS / 4];
+    const uint32_t g = threadIdx.x >> 2;
     XYZZ acc = XYZZ::inf();
-    for (uint32_t g = 0; g < count; g++) {
-        XYZZ q = ld_xyzz(&in[(size_t)g * rank_stride + blockIdx.x]);
-        xyzz_add(acc, q);
+    for (uint32_t r = g; r < count; r += COMBINE_THREADS / 4) {
+        XYZZ q = ld_xyzz(&in[(size_t)r * rank_stride + blockIdx.x]);
+        xyzz_add_coop(acc, q);
     }
-    st_xyzz(out + blockIdx.x, acc);
+    XYZZ tot = block_tree_sum_coop<COMBINE_THREADS>(acc, sh);
+    if (threadIdx.x == 0) st_xyzz(out + blockIdx.x, tot);
 }
 
 // --------------------------------------------------------------------------
@@ -775,7 +783,10 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.nb = 1u << (s->c - 1);
     // threads: a whole number of waves of (SMs * 3 blocks * 128 threads)
     size_t wave = (size_t)c.sm_count * 3 * 128;
-    size_t target_chunk = 48;
+    // entries per accumulate thread: 48 (five waves at 2^20 x 13 windows) balances the accumulate kernel best; from ~2^21
+    // points on, the boundary partials (two per thread) make the fix-up the larger term and longer chunks win
+    // (2^21: 12.08 ms at 80 vs 12.25 ms at 48; profiles/r02e_msm_tail_knobs.log)
+    size_t target_chunk = p.total > ((size_t)1 << 24) ? 80 : 48;
     if (const char* e = getenv("KZGB_MSM_CHUNK")) target_chunk = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : target_chunk;
     size_t waves = (p.total + wave * target_chunk - 1) / (wave * target_chunk);
     if (waves < 1) waves = 1;
@@ -803,7 +814,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.nslots = 2 * p.nthreads;
     p.off_partials = take((size_t)p.nslots * sizeof(XYZZ));
     p.off_meta = take((size_t)p.nslots * sizeof(PartialMeta));
-    p.fix_slots = 2 * (p.nslots / FIX_F + 1) + 2;
+    p.fix_slots = 2 * (p.nslots / FIX_F_MIN + 1) + 2;
     p.off_fixp0 = take((size_t)p.fix_slots * sizeof(XYZZ));
     p.off_fixp1 = take((size_t)p.fix_slots * sizeof(XYZZ));
     p.off_fixm0 = take((size_t)p.fix_slots * sizeof(PartialMeta));
@@ -910,14 +921,25 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
         XYZZ* pbuf[2] = {(XYZZ*)(w + p.off_fixp0), (XYZZ*)(w + p.off_fixp1)};
         PartialMeta* mbuf[2] = {(PartialMeta*)(w + p.off_fixm0), (PartialMeta*)(w + p.off_fixm1)};
         int which = 0;
+        // Level 0 is dense (two partials per accumulate thread): its cost is the chain of full additions per thread.
+        // Measured on B200 (profiles/r02e_msm_tail_knobs.log): 8 slots per thread (4 additions) beats 16 at every size
+        // (2^20: 0.33 vs 0.39 ms, 2^21: 0.73 vs 0.77 ms); sparser levels keep 16.  Must be even: the natural pairs
+        // (2a+1, 2a+2) may not straddle a range boundary at t*F + 1.
+        uint32_t F0 = 8;
+        if (const char* e = getenv("KZGB_MSM_FIX_F")) {
+            uint32_t f = (uint32_t)atoi(e);
+            f += f & 1;
+            if (f >= FIX_F_MIN && f <= FIX_F_MAX) F0 = f;
+        }
         for (int level = 0;; level++) {
-            uint32_t nth = nslots_in > 1 ? (nslots_in - 1 + FIX_F - 1) / FIX_F : 1;
+            const uint32_t F = level == 0 ? F0 : FIX_F;
+            uint32_t nth = nslots_in > 1 ? (nslots_in - 1 + F - 1) / F : 1;
             if (level == 0)
                 msm_fixup_level_kernel<false><<<div_up(nth, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets,
-                                                                                    pbuf[which], mbuf[which], nth);
+                                                                                    pbuf[which], mbuf[which], nth, F);
             else
                 msm_fixup_level_kernel<true><<<div_up((size_t)nth * 4, 128), 128, 0, stream>>>(pin, min_, nslots_in, buckets,
-                                                                                         pbuf[which], mbuf[which], nth);
+                                                                                         pbuf[which], mbuf[which], nth, F);
             KZG_LAUNCHED();
             if (nth == 1) break;
             pin = pbuf[which];
@@ -986,8 +1008,8 @@ int msm_finish(const XYZZ* d_xyzz, void* d_out, int mode, cudaStream_t stream, u
 }
 
 int msm_combine(const void* d_partials_xyzz, uint32_t count, void* d_out_xyzz, cudaStream_t stream, uint32_t items) {
-    msm_combine_kernel<<<items, 32, 0, stream>>>((const XYZZ*)d_partials_xyzz, count, (XYZZ*)d_out_xyzz,
-                                                 items > 1 ? items : 1);
+    msm_combine_kernel<<<items, COMBINE_THREADS, 0, stream>>>((const XYZZ*)d_partials_xyzz, count, (XYZZ*)d_out_xyzz,
+                                                              items > 1 ? items : 1);
     KZG_LAUNCHED();
     return KZGB_OK;
 }

@@ -70,5 +70,6 @@ void srs_register(kzgb_srs* s);                 // live-handle list (api_core.cu
 void srs_unregister(kzgb_srs* s);
 void srs_release_device(kzgb_srs* s);           // frees everything on the device, marks the handle dead
 void comm_shutdown();                           // multi-GPU communicator (comm.cu)
+void poly_cache_shutdown();                     // parked kzgb_poly buffers (api_handle.cu)
 int jac_to_affine_dev(const void* d_jac, void* d_aff, size_t n, cudaStream_t stream);
 }  // namespace kzg

@@ -233,6 +233,27 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     }
 }
 
+// First pass of a transform whose input is zero beyond its first nz entries (nz <= the pass's stride S): every
+// R-point column transform then has at most ONE non-zero input (digit 0), so its R outputs are that input times the
+// inter-pass twiddle, out[k*S + low] = a[low] * omega_N^(k*low) for low < nz, and zero elsewhere (the caller clears the
+// destination).  Used for the vanishing polynomial Z (m + 1 coefficients in a 2^20-point transform, batched.cu).
+__global__ void __launch_bounds__(256) ntt_sparse_first_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out,
+                                                                    const Fr* __restrict__ tw, uint32_t log_n, uint32_t log_r,
+                                                                    uint32_t nz, uint32_t inverse) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = idx / nz, low = idx % nz;
+    if (k >= (1u << log_r)) return;
+    Fr v = ldg_fr(&in[low]);
+    const uint32_t ex = k * low;              // < 2^log_r * S = N: no wrap before the mask in twiddle()
+    if (ex != 0) {
+        bool neg;
+        Fr w = twiddle(tw, ex, log_n, inverse, neg);
+        v = v * w;
+        if (neg) v = v.neg();
+    }
+    sts_fr(&out[((size_t)k << (log_n - log_r)) + low], v);
+}
+
 // tw[i] = omega^i, i < count
 __global__ void ntt_twiddle_kernel(Fr* __restrict__ out, Fr omega, size_t count) {
     constexpr int CH = 16;
@@ -365,7 +386,7 @@ int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c,
 // In-place (for the caller) transform of d_data[0 .. 2^log_n); d_tmp is a same-size scratch buffer
 // (unused when the plan has one pass).
 int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream, uint32_t batch,
-            const Fr* scale) {
+            const Fr* scale, uint32_t nonzero_prefix) {
     if (log_n >= 32) return KZGB_DEGREE_TOO_LARGE;  // ft.rs:67-69
     if (log_n == 0 && !scale) return KZGB_OK;        // size-1 transform is the identity (minv = 1)
     if (batch == 0) return KZGB_OK;
@@ -425,6 +446,15 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         else if (j == 0) { src = d_data; dst = d_tmp; }
         else if (last) { src = d_tmp; dst = d_data; }
         else { src = d_tmp; dst = d_tmp; }
+        if (j == 0 && !last && batch == 1 && nonzero_prefix > 0 && nonzero_prefix <= (1u << log_s)) {
+            // sparse input (only the first nonzero_prefix entries are non-zero): the first pass degenerates
+            KZG_CUDA(cudaMemsetAsync(dst, 0, (size_t)32 << log_n, stream));
+            const uint32_t work = nonzero_prefix << p.log_r;
+            ntt_sparse_first_pass_kernel<<<div_up(work, 256), 256, 0, stream>>>(src, dst, tw, log_n, p.log_r, nonzero_prefix,
+                                                                                p.inverse);
+            KZG_LAUNCHED();
+            continue;
+        }
         dim3 grid((unsigned)tiles, batch);
         if (last) ntt_pass_kernel<true, false><<<grid, threads, smem, stream>>>(src, dst, tw, p, minv, NttScatter{});
         else ntt_pass_kernel<false, false><<<grid, threads, smem, stream>>>(src, dst, tw, p, minv, NttScatter{});

@@ -5,8 +5,10 @@
 #include "field.cuh"
 
 namespace kzg {
+// nonzero_prefix > 0: the caller guarantees d_data[i] == 0 for i >= nonzero_prefix; when the prefix fits inside the first
+// pass's stride that pass is replaced by a direct evaluation (see ntt_sparse_first_pass_kernel)
 int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t stream, uint32_t batch = 1,
-            const Fr* scale = nullptr);
+            const Fr* scale = nullptr, uint32_t nonzero_prefix = 0);
 // Fused four-step exchange: destination row matrices of every rank (peer[rank] is local, the others are CUDA-IPC
 // mappings valid on this device); see ntt.cu / comm.cu.
 constexpr int NTT_MAX_PEERS = 16;

@@ -37,11 +37,17 @@ KZG_DI void st_fr(Fr* p, const Fr& v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// pw[i] = x^(SCAN_L * 2^i)
+// pw[i] = x^(SCAN_L * 2^i), i < SCAN_POWS_USED: the in-block scan reads pw[0..8), the block-carry pass pw[8].
+// (One thread, a chain of dependent squarings at ~0.6 us each: computing all SCAN_POWS = 48 entries of the table cost
+// 30 us of a 120 us division; the nine that are read cost 8.)
+constexpr int SCAN_POWS_USED = 9;
 __global__ void scan_powers_kernel(const Fr* __restrict__ x, Fr* __restrict__ pw) {
     if (threadIdx.x || blockIdx.x) return;
-    Fr v = x->pow_u64(SCAN_L);
-    for (int i = 0; i < SCAN_POWS; i++) {
+    Fr v = *x;
+#pragma unroll 1
+    for (int i = 1; i < SCAN_L; i <<= 1) v = v.sqr();   // x^SCAN_L (SCAN_L is a power of two)
+#pragma unroll 1
+    for (int i = 0; i < SCAN_POWS_USED; i++) {
         pw[i] = v;
         v = v.sqr();
     }

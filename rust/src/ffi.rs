@@ -11,6 +11,15 @@ use std::sync::Once;
 pub struct kzgb_srs {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct kzgb_poly {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct kzgb_ntt4_plan {
+    _private: [u8; 0],
+}
+pub const KZGB_COMM_ID_BYTES: usize = 128;
 
 pub const KZGB_OK: c_int = 0;
 pub const KZGB_POINT_NOT_ON_POLYNOMIAL: c_int = 1;
@@ -33,6 +42,26 @@ extern "C" {
                                 r_out: *mut Scalar, r_len: *mut usize, w_out: *mut G1Affine) -> c_int;
     pub fn kzgb_div_by_omega_i(evals: *const Scalar, log_d: u32, i: usize, q_out: *mut Scalar) -> c_int;
     pub fn kzgb_witness_eval(lagrange_srs: *mut kzgb_srs, evals: *const Scalar, log_d: u32, i: usize, out: *mut G1Affine) -> c_int;
+    // device-resident polynomial handles (one upload, many calls)
+    pub fn kzgb_poly_upload(coeffs: *const Scalar, n: usize, out: *mut *mut kzgb_poly) -> c_int;
+    pub fn kzgb_poly_free(poly: *mut kzgb_poly) -> c_int;
+    pub fn kzgb_poly_commit(srs: *mut kzgb_srs, poly: *mut kzgb_poly, m: usize, out: *mut G1Affine) -> c_int;
+    pub fn kzgb_poly_witness(srs: *mut kzgb_srs, poly: *mut kzgb_poly, n: usize, x: *const Scalar, y: *const Scalar, out: *mut G1Affine) -> c_int;
+    pub fn kzgb_poly_witness_batched(srs: *mut kzgb_srs, poly: *mut kzgb_poly, n: usize, xs: *const Scalar, ys: *const Scalar, m: usize,
+                                     r_out: *mut Scalar, r_len: *mut usize, w_out: *mut G1Affine) -> c_int;
+    pub fn kzgb_poly_witness_eval(lagrange_srs: *mut kzgb_srs, evals: *mut kzgb_poly, log_d: u32, i: usize, out: *mut G1Affine) -> c_int;
+    // multi-GPU (one process per GPU; NCCL inside the library)
+    pub fn kzgb_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn kzgb_comm_init(rank: c_int, world: c_int, id: *const u8) -> c_int;
+    pub fn kzgb_comm_destroy() -> c_int;
+    pub fn kzgb_srs_generate(kind: c_int, secret: *const Scalar, total: usize, first: usize, count: usize, window_bits: c_int,
+                             out: *mut *mut kzgb_srs) -> c_int;
+    pub fn kzgb_msm_g1_sharded(shard: *mut kzgb_srs, scalars: *const Scalar, m: usize, out: *mut G1Affine) -> c_int;
+    pub fn kzgb_msm_g1_sharded_batch(shard: *mut kzgb_srs, scalars: *const *const Scalar, ms: *const usize, count: usize,
+                                     out: *mut G1Affine) -> c_int;
+    pub fn kzgb_ntt4_plan_create(log_n: u32, log_n1: u32, out: *mut *mut kzgb_ntt4_plan) -> c_int;
+    pub fn kzgb_ntt4_plan_destroy(plan: *mut kzgb_ntt4_plan) -> c_int;
+    pub fn kzgb_ntt_fr_sharded(plan: *mut kzgb_ntt4_plan, input: *const Scalar, out: *mut Scalar, inverse: c_int, gather: c_int) -> c_int;
     #[allow(dead_code)]
     pub fn kzgb_shutdown() -> c_int;
     #[allow(dead_code)]
@@ -57,7 +86,7 @@ pub fn check(status: c_int, what: &str) -> c_int {
 /// clones through an `Arc`; safe to cache because provers borrow `&'params KZGParams` (coeff_form.rs:39).
 pub struct Srs(*mut kzgb_srs);
 unsafe impl Send for Srs {}
-unsafe impl Sync for Srs {} // the library serialises calls with an internal mutex
+unsafe impl Sync for Srs {} // calls on one handle serialise on the handle's own lock; different handles run concurrently
 
 impl Srs {
     pub fn new(points: &[G1Projective]) -> Self {
@@ -77,5 +106,29 @@ impl Srs {
 impl Drop for Srs {
     fn drop(&mut self) {
         unsafe { kzgb_srs_destroy(self.0) };
+    }
+}
+
+/// Device-resident copy of a polynomial's coefficients (`kzgb_poly`): `commit` -> `create_witness` ->
+/// `create_witness_batched` on the same `&Polynomial` then upload it once instead of once per call.
+pub struct DevicePoly(*mut kzgb_poly, usize);
+unsafe impl Send for DevicePoly {}
+unsafe impl Sync for DevicePoly {}
+impl DevicePoly {
+    pub fn new(coeffs: &[Scalar]) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { kzgb_poly_upload(coeffs.as_ptr(), coeffs.len(), &mut h) }, "kzgb_poly_upload");
+        DevicePoly(h, coeffs.len())
+    }
+    pub fn raw(&self) -> *mut kzgb_poly {
+        self.0
+    }
+    pub fn len(&self) -> usize {
+        self.1
+    }
+}
+impl Drop for DevicePoly {
+    fn drop(&mut self) {
+        unsafe { kzgb_poly_free(self.0) };
     }
 }

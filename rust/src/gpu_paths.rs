@@ -78,8 +78,7 @@ pub fn create_witness_batched(srs: &Srs, polynomial: &Polynomial, xs: &[Scalar],
         ffi::KZGB_POINT_NOT_ON_POLYNOMIAL => Err(KZGError::PointNotOnPolynomial), // coeff_form.rs:96
         _ => {
             r.truncate(r_len);
-            // m >= 2: declared degree m-1 (Mul, polynomial.rs:484); m == 1: X + (y - x), degree 1 (polynomial.rs:244-247)
-            Ok((Polynomial::new_from_coeffs(r, r_len - 1), w))
+            Ok((interpolant_shape(r, xs.len()), w))
         }
     }
 }
@@ -89,4 +88,41 @@ pub fn create_witness_eval(lagrange: &Srs, evals: &[Scalar], log_d: u32, i: usiz
     let mut out = G1Affine::default();
     ffi::check(unsafe { ffi::kzgb_witness_eval(lagrange.raw(), evals.as_ptr(), log_d, i, &mut out) }, "kzgb_witness_eval");
     out
+}
+
+/// The shape the reference's tree recursion gives the interpolant (polynomial.rs:303-365): below 258 points exactly m
+/// coefficients with declared degree m - 1 (m == 1: X + (y - x), degree 1, polynomial.rs:244-247); from 258 points on the
+/// top-level `best_mul` takes the `fft_mul` path (polynomial.rs:167-191), whose result keeps the whole padded transform
+/// (2^k >= m + 1 coefficients) with a re-measured degree (`Polynomial::new`).
+fn interpolant_shape(mut r: Vec<Scalar>, m: usize) -> Polynomial {
+    if m >= 258 {
+        r.resize((m + 1).next_power_of_two(), Scalar::default());
+        Polynomial::new(r)
+    } else {
+        let d = r.len() - 1;
+        Polynomial::new_from_coeffs(r, d)
+    }
+}
+
+/// `commit` over a point-sharded SRS (one process per GPU, `ffi::kzgb_comm_init` done at start-up): every rank passes
+/// its slice of the coefficients; the library all-gathers the 192-byte partial sums over NCCL and every rank returns
+/// the full commitment.  Same bytes as `commit` on one GPU.
+pub fn multi_exp_sharded(shard: &Srs, scalars_shard: &[Scalar]) -> G1Affine {
+    let mut out = G1Affine::default();
+    ffi::check(unsafe { ffi::kzgb_msm_g1_sharded(shard.raw(), scalars_shard.as_ptr(), scalars_shard.len(), &mut out) }, "kzgb_msm_g1_sharded");
+    out
+}
+
+/// `commit` / `create_witness` on a resident copy of the polynomial (`ffi::DevicePoly`): no per-call upload.
+pub fn commit_resident(srs: &Srs, poly: &ffi::DevicePoly, num_coeffs: usize) -> G1Affine {
+    let mut out = G1Affine::default();
+    ffi::check(unsafe { ffi::kzgb_poly_commit(srs.raw(), poly.raw(), num_coeffs, &mut out) }, "kzgb_poly_commit");
+    out
+}
+pub fn create_witness_resident(srs: &Srs, poly: &ffi::DevicePoly, num_coeffs: usize, (x, y): (Scalar, Scalar)) -> Result<KZGWitness, KZGError> {
+    let mut out = G1Affine::default();
+    match ffi::check(unsafe { ffi::kzgb_poly_witness(srs.raw(), poly.raw(), num_coeffs, &x, &y, &mut out) }, "kzgb_poly_witness") {
+        ffi::KZGB_POINT_NOT_ON_POLYNOMIAL => Err(KZGError::PointNotOnPolynomial),
+        _ => Ok(out),
+    }
 }
