@@ -42,6 +42,7 @@ struct NttPassParams {
     uint32_t tw_shift;   // inter-pass twiddle exponent = (k_j * (low_offset + low)) << tw_shift
     uint32_t low_offset; // global index of this slab's first column (four-step, multi-GPU); 0 otherwise
     uint32_t apply_scale; // last pass: multiply by `minv`
+    uint32_t swz;        // non-last passes: XOR-swizzle the shared-memory slots (see ntt_pass_kernel)
     uint64_t batch_stride; // elements between consecutive vectors of a batch (gridDim.y vectors)
 };
 
@@ -109,7 +110,17 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     // (the butterfly stages, the final read) stay conflict-free because the XOR permutes each aligned group of 8.
     const uint32_t sw_shift = (LAST && p.log_r >= 3 && p.log_t >= 3) ? p.log_r - 3 : 0;
     const uint32_t sw_mask = (LAST && p.log_r >= 3 && p.log_t >= 3) ? 7u : 0u;
-    auto SW = [&](uint32_t row, uint32_t col) { return (row << p.log_t) + (col ^ ((row >> sw_shift) & sw_mask)); };
+    // Non-last passes: a tile row holds only T = 2^log_t consecutive elements (T = 4 for the usual 2^8 x 4 tile, T = 1
+    // for a 2^10-point pass), so a quarter-warp touches SEVERAL rows per 128-byte bank phase and the row pattern decides
+    // the conflicts: bit-reversed rows while staging, rows 4*gg in the first radix-4 step -- all multiples of 32 or 4
+    // slots, i.e. the same bank group (ncu, round 1: 3.5 M conflicts per pass).  Folding the upper slot bits onto the low
+    // three (slot ^= slot>>3 ^ slot>>6 ^ slot>>9, mod 8) makes every power-of-two stride conflict-free.
+    const bool gswz = !LAST && p.swz;
+    auto SW = [&](uint32_t row, uint32_t col) {
+        uint32_t slot = (row << p.log_t) + (col ^ ((row >> sw_shift) & sw_mask));
+        if (gswz) slot ^= ((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u;
+        return slot;
+    };
     const uint64_t tile = blockIdx.x;
     // batched transforms: blockIdx.y selects one of gridDim.y independent length-2^log_n vectors
     in += (size_t)blockIdx.y * p.batch_stride;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
             uint32_t d = e >> p.log_t, tl = e & (T - 1);
             uint32_t dr = __brev(d) >> (32 - p.log_r);
             if (p.log_r == 0) dr = 0;
-            sm_st(sm, (dr << p.log_t) + tl, E, lds_fr(&in[base + ((uint64_t)d << p.log_s) + tl]));
+            sm_st(sm, SW(dr, tl), E, lds_fr(&in[base + ((uint64_t)d << p.log_s) + tl]));
         }
     } else {
         if (p.npass > 1) {
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     if (!LAST) {
         for (uint32_t e = tid; e < E; e += nthr) {
             uint32_t kj = e >> p.log_t, tl = e & (T - 1);
-            Fr v = sm_ld(sm, e, E);
+            Fr v = sm_ld(sm, SW(kj, tl), E);
             uint64_t ex = ((uint64_t)kj * (p.low_offset + low0 + tl)) << p.tw_shift;
             if (ex != 0) {
                 bool neg;
@@ -294,6 +305,14 @@ int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out) {
     return KZGB_OK;
 }
 
+// Experiment knob KZGB_NTT_SWZ=1: XOR-swizzled slots in the non-last passes.  Bit-exact, removes the bank conflicts ncu
+// reports for those passes, and changes nothing measurable (2^22: 0.921 vs 0.914 ms, 2^20: 0.244 vs 0.248 ms;
+// profiles/r02i_ntt_sweep.log): shared-memory bandwidth is not what limits the passes.  Off by default.
+static uint32_t ntt_swizzle_enabled() {
+    const char* e = getenv("KZGB_NTT_SWZ");
+    return (e && *e == '1') ? 1u : 0u;
+}
+
 struct NttPlan {
     int npass;
     uint32_t log_r[3];
@@ -311,9 +330,19 @@ static NttPlan ntt_plan(uint32_t log_n) {
         }
     }
     // radix-4 steps cover two stages at a time, so even radices avoid the extra radix-2 stage: make every radix
-    // even where the total allows it (2^22 -> 8,8,6: 0.935 ms vs 0.969 ms for 8,7,7)
-    pl.npass = log_n <= 10 ? 1 : (log_n <= 20 ? 2 : 3);
+    // even where the total allows it (2^22 -> 8,8,6: 0.935 ms vs 0.969 ms for 8,7,7).
+    // Up to 2^20 the grid of a pass is only a wave or two of tiles, so tile count matters as much as arithmetic:
+    // 512-element tiles (ntt_run) and, from 2^18 on, three passes of radix <= 2^8 instead of two of radix 2^9..2^10
+    // (measured, profiles/r02i_ntt_sweep_b.log: 2^16 0.033 vs 0.055 ms, 2^18 0.074 vs 0.078, 2^19 0.130 vs 0.147,
+    // 2^20 0.224 vs 0.248; from 2^21 on the round-1 plan and 1024-element tiles stay best).
     pl.log_r[0] = pl.log_r[1] = pl.log_r[2] = 0;
+    if (log_n >= 18 && log_n <= 20) {
+        pl.npass = 3;
+        pl.log_r[0] = pl.log_r[1] = log_n == 18 ? 6 : 8;
+        pl.log_r[2] = log_n - 2 * pl.log_r[0];
+        return pl;
+    }
+    pl.npass = log_n <= 10 ? 1 : (log_n <= 20 ? 2 : 3);
     uint32_t remaining = log_n;
     for (int j = 0; j < pl.npass; j++) {
         uint32_t left = (uint32_t)(pl.npass - j);
@@ -367,6 +396,7 @@ int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c,
     p.low_offset = col_offset;
     p.apply_scale = 0;
     p.batch_stride = 0;
+    p.swz = ntt_swizzle_enabled();
     p.log_t = std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, log_c);
     size_t tiles = ((size_t)1 << log_c) >> p.log_t;
     size_t smem = (size_t)32 << (p.log_r + p.log_t);
@@ -411,7 +441,7 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
     // 1024-element tiles (32 KiB) with 128 threads: six resident blocks per SM instead of three 64 KiB ones -- same
     // occupancy, but finer-grained blocks (shorter barrier phases, smaller last-wave loss): 2^22 0.94 -> 0.91 ms,
     // 2^20 0.27 -> 0.25 ms, 2^24 3.95 -> 3.77 ms.  Knob for experiments: KZGB_NTT_TILE="tile_log,threads".
-    uint32_t tile_log = 10, threads = 128;
+    uint32_t tile_log = log_n <= 20 ? 9 : 10, threads = 128;
     if (const char* e = getenv("KZGB_NTT_TILE")) {
         unsigned a = 0, b = 0;
         if (sscanf(e, "%u,%u", &a, &b) == 2 && a >= 8 && a <= 11 && (b == 64 || b == 128 || b == 256)) { tile_log = a; threads = b; }
@@ -430,6 +460,7 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         p.inverse = inverse ? 1 : 0;
         p.tw_shift = log_n - p.log_nj;
         p.low_offset = 0;
+        p.swz = ntt_swizzle_enabled();
         p.batch_stride = (uint64_t)1 << log_n;
         bool last = (j == pl.npass - 1);
         p.apply_scale = (last && apply_scale) ? 1 : 0;
