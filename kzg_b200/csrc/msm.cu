@@ -32,6 +32,12 @@
 #define KZG_OUTLINE_FQ_MUL 1
 #endif
 
+// The next table point of the accumulation is staged through shared memory with cp.async (default); the round-1
+// register-staged software pipeline is kept behind -DKZG_MSM_REG_PREFETCH (measured: 4.89 vs 4.84 ms, r02j logs).
+#ifndef KZG_MSM_REG_PREFETCH
+#define KZG_MSM_SMEM_PREFETCH 1
+#endif
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -90,7 +96,11 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ 
 // --------------------------------------------------------------------------
 constexpr uint32_t SLOT_EMPTY = 0xffffffffu;
 
-__device__ __noinline__ void xyzz_madd_rare(XYZZ& acc, const Fq& x2, const Fq& y2, bool same) {
+// The P == 0 cases (the incoming point equals the accumulator or its negative).  Inline on purpose: as an out-of-line
+// function taking `acc` by reference it forced the accumulator into a 336-byte stack frame, and the hot loop then moved
+// it through local memory on every addition (ncu, round 1/2: 42 M LDL + 66 M STL warp instructions per launch, 5.5 % of
+// the kernel's instructions).  With the field products out of line the inlined doubling is a dozen CALLs, not 60 KB.
+KZG_DI void xyzz_madd_rare(XYZZ& acc, const Fq& x2, const Fq& y2, bool same) {
     if (same) acc = xyzz_dbl_affine(x2, y2);
     else acc = XYZZ::inf();
 }
@@ -126,11 +136,28 @@ struct PartialMeta {
     uint32_t is_start; // the bucket's segment begins inside the producing thread's chunk
 };
 
-__global__ void __launch_bounds__(128, 3)
+#ifdef KZG_MSM_SMEM_PREFETCH
+// The next table point travels global -> shared memory with cp.async (LDGSTS: no register staging) while the current
+// one is added, instead of sitting in 24 registers across the ten out-of-line field products of the addition.
+KZG_DI void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+KZG_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KZG_DI void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+#endif
+
+#ifndef KZG_MSM_ACC_BLOCKS
+#define KZG_MSM_ACC_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, KZG_MSM_ACC_BLOCKS)
 msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                       const Affine* __restrict__ table, uint64_t total, const unsigned long long* __restrict__ zero_count,
                       uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
                       PartialMeta* __restrict__ meta, uint32_t nthreads) {
+#ifdef KZG_MSM_SMEM_PREFETCH
+    __shared__ uint4 pstage[2][6][128];   // [buffer][16-byte word of the point][thread]: 24 KiB, conflict-free columns
+#endif
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     const uint64_t nvalid = total - *zero_count;
@@ -145,16 +172,45 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
         XYZZ acc = XYZZ::inf();
         // software pipeline: the next point is in flight while the current one is added
         uint32_t v = vals[start];
+#ifdef KZG_MSM_SMEM_PREFETCH
+        auto prefetch = [&](int buf, uint32_t val) {
+            const uint4* src = reinterpret_cast<const uint4*>(&table[val & 0x7fffffffu]);
+#pragma unroll
+            for (int w = 0; w < 6; w++) cp_async16(&pstage[buf][w][threadIdx.x], src + w);
+        };
+        prefetch(0, v);
+        cp_async_commit();
+        int buf = 0;
+#else
         Affine p = ldcs_affine(&table[v & 0x7fffffffu]);
+#endif
         for (uint64_t pos = start; pos < end; pos++) {
             uint32_t k = cur, vn = 0;
-            Affine pn = p;
             bool more = pos + 1 < end;
+#ifdef KZG_MSM_SMEM_PREFETCH
+            if (more) {
+                k = keys[pos + 1];
+                vn = vals[pos + 1];
+                prefetch(buf ^ 1, vn);
+            }
+            cp_async_commit();             // one group per iteration (empty after the last point)
+            cp_async_wait_all_but_one();   // => the group of THIS iteration's point has landed
+            Affine p;
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                const uint4 a = pstage[buf][w][threadIdx.x], b = pstage[buf][3 + w][threadIdx.x];
+                p.x.l[4 * w] = a.x; p.x.l[4 * w + 1] = a.y; p.x.l[4 * w + 2] = a.z; p.x.l[4 * w + 3] = a.w;
+                p.y.l[4 * w] = b.x; p.y.l[4 * w + 1] = b.y; p.y.l[4 * w + 2] = b.z; p.y.l[4 * w + 3] = b.w;
+            }
+            buf ^= 1;
+#else
+            Affine pn = p;
             if (more) {
                 k = keys[pos + 1];
                 vn = vals[pos + 1];
                 pn = ldcs_affine(&table[vn & 0x7fffffffu]);
             }
+#endif
             if (!p.is_inf()) {
                 Fq y = (v >> 31) ? p.y.neg() : p.y;
                 madd_hot(acc, p.x, y);
@@ -173,7 +229,9 @@ msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restr
                 first = false;
             }
             v = vn;
+#ifndef KZG_MSM_SMEM_PREFETCH
             p = pn;
+#endif
         }
         bool ended_here = (end == nvalid) || (keys[end] != cur);
         if (cur_started_here && ended_here) {
@@ -782,7 +840,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.total = m * (size_t)s->nwin;
     p.nb = 1u << (s->c - 1);
     // threads: a whole number of waves of (SMs * 3 blocks * 128 threads)
-    size_t wave = (size_t)c.sm_count * 3 * 128;
+    size_t wave = (size_t)c.sm_count * KZG_MSM_ACC_BLOCKS * 128;
     // entries per accumulate thread: 48 (five waves at 2^20 x 13 windows) balances the accumulate kernel best; from ~2^21
     // points on, the boundary partials (two per thread) make the fix-up the larger term and longer chunks win
     // (2^21: 12.08 ms at 80 vs 12.25 ms at 48; profiles/r02e_msm_tail_knobs.log)
