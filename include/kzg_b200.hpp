@@ -147,6 +147,17 @@ public:
         check(st, "kzgb_witness_batched");
         if (st == KZGB_POINT_NOT_ON_POLYNOMIAL) return {std::nullopt, KZGError::PointNotOnPolynomial};
         r.resize(r_len);
+        // the shape the reference's tree recursion gives r (polynomial.rs:303-365): from 258 points on, the top-level
+        // best_mul takes the fft_mul path (polynomial.rs:167-191): vector padded to 2^k >= m + 1, degree re-measured
+        if (xs.size() >= 258) {
+            size_t size = 1;
+            while (size < xs.size() + 1) size *= 2;
+            r.resize(size, Scalar{});
+            size_t deg = r_len - 1;
+            auto is_zero = [](const Scalar& v) { return (v.l[0] | v.l[1] | v.l[2] | v.l[3]) == 0; };
+            while (deg > 0 && is_zero(r[deg])) deg--;
+            return {KZGBatchWitness{Polynomial::new_from_coeffs(std::move(r), deg), w}, {}};
+        }
         return {KZGBatchWitness{Polynomial::new_from_coeffs(std::move(r), r_len - 1), w}, {}};
     }
 
