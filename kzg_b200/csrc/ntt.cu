@@ -43,6 +43,7 @@ struct NttPassParams {
     uint32_t low_offset; // global index of this slab's first column (four-step, multi-GPU); 0 otherwise
     uint32_t apply_scale; // last pass: multiply by `minv`
     uint32_t swz;        // non-last passes: XOR-swizzle the shared-memory slots (see ntt_pass_kernel)
+    uint32_t fold;       // inter-pass twiddles folded into the NEXT pass's butterflies (see ntt_pass_kernel)
     uint64_t batch_stride; // elements between consecutive vectors of a batch (gridDim.y vectors)
 };
 
@@ -128,9 +129,19 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     uint64_t base = 0;      // non-last: address of (d = 0, tl = 0)
     uint64_t low0 = 0;
     uint64_t k10 = 0, k2 = 0;
+    // Folded twiddles (p.fold): instead of multiplying every output of pass j by omega_N^(k_j * low) and starting the
+    // next pass with unit twiddles, pass j+1 transforms its digit as a COSET transform with the shifted root
+    // g = omega_N^(S * kappa), kappa = k_1 + R_1 k_2 + ... = the output digits already fixed: stage s (m = 2^s) then uses
+    //      e = j * N/(2m) + kappa * N_j/(2m),   N_j = R_j * S_j
+    // as its twiddle exponent -- one table lookup as before -- and the separate multiplication disappears: N fewer
+    // products per pass boundary, N/2 more because the first stage of the later passes is no longer trivial
+    // (2^22 = 2^8 2^8 2^6: 10.5 N instead of 11.5 N products).  Index algebra checked against the naive DFT for every
+    // 1-3 pass plan up to 2^8 in scripts/ntt_fold_model.py.
+    uint32_t kap_tile = 0;  // non-last passes: kappa of the whole tile (= hi: 0 in pass 1, k_1 in pass 2 of 3)
     if (!LAST) {
         const uint64_t tiles_per_hi = (1ull << p.log_s) >> p.log_t;
         const uint64_t hi = tile / tiles_per_hi;
+        if (p.fold) kap_tile = (uint32_t)hi;
         low0 = (tile % tiles_per_hi) << p.log_t;
         base = (hi << p.log_nj) + low0;
         for (uint32_t e = tid; e < E; e += nthr) {
@@ -160,12 +171,20 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     if (p.log_r & 1) {
         for (uint32_t b = tid; b < E / 2; b += nthr) {
             uint32_t tl = b & (T - 1), bb = b >> p.log_t;
-            uint32_t i0 = SW(bb << 1, tl);   // m = 1: pairs (2bb, 2bb+1), twiddle 1
+            uint32_t i0 = SW(bb << 1, tl);   // m = 1: pairs (2bb, 2bb+1), twiddle 1 (folded: g^(R/2))
             uint32_t i1 = SW((bb << 1) + 1, tl);
             Fr u = sm_ld(sm, i0, E);
             Fr t = sm_ld(sm, i1, E);
-            sm_st(sm, i0, E, u + t);
-            sm_st(sm, i1, E, u - t);
+            const uint32_t kap = LAST ? (p.fold ? (uint32_t)(k10 + tl) + ((uint32_t)k2 << p.log_r1) : 0u) : kap_tile;
+            const uint32_t e0 = (kap << p.log_nj) >> 1;
+            bool neg = false;
+            if (e0 != 0) {
+                Fr w = twiddle(tw, e0, p.log_n, p.inverse, neg);
+                t = t * w;
+            }
+            Fr a = u + t, c = u - t;
+            sm_st(sm, i0, E, neg ? c : a);
+            sm_st(sm, i1, E, neg ? a : c);
         }
         __syncthreads();
         s = 1;
@@ -178,28 +197,32 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
             uint32_t k = (gg >> s) << (s + 2);
             const uint32_t i0 = SW(k + j, tl), i1 = SW(k + j + m, tl), i2 = SW(k + j + 2 * m, tl), i3 = SW(k + j + 3 * m, tl);
             Fr x0 = sm_ld(sm, i0, E), x1 = sm_ld(sm, i1, E), x2 = sm_ld(sm, i2, E), x3 = sm_ld(sm, i3, E);
-            // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m)
+            const uint32_t kap = LAST ? (p.fold ? (uint32_t)(k10 + tl) + ((uint32_t)k2 << p.log_r1) : 0u) : kap_tile;
+            const uint32_t kbase = kap << p.log_nj;     // kappa * N_j  (< N)
+            // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m + kappa * N_j/2m)
             {
                 bool neg = false;
-                if (j != 0) {
-                    Fr w = twiddle(tw, j << (p.log_n - s - 1), p.log_n, p.inverse, neg);
+                const uint32_t e1 = (j << (p.log_n - s - 1)) + (kbase >> (s + 1));
+                if (e1 != 0) {
+                    Fr w = twiddle(tw, e1, p.log_n, p.inverse, neg);
                     x1 = x1 * w;
                     x3 = x3 * w;
                 }
                 Fr a = x0 + x1, c = x0 - x1, d = x2 + x3, e = x2 - x3;
                 x0 = neg ? c : a; x1 = neg ? a : c; x2 = neg ? e : d; x3 = neg ? d : e;
             }
-            // stage s+1: (x0,x2) with w^(j * N/4m), (x1,x3) with w^((j+m) * N/4m)
+            // stage s+1: (x0,x2) with w^(j * N/4m + kappa * N_j/4m), (x1,x3) with w^((j+m) * N/4m + kappa * N_j/4m)
             {
                 bool neg = false;
-                if (j != 0) {
-                    Fr w = twiddle(tw, j << (p.log_n - s - 2), p.log_n, p.inverse, neg);
+                const uint32_t e2 = (j << (p.log_n - s - 2)) + (kbase >> (s + 2));
+                if (e2 != 0) {
+                    Fr w = twiddle(tw, e2, p.log_n, p.inverse, neg);
                     x2 = x2 * w;
                 }
                 Fr a = x0 + x2, c = x0 - x2;
                 x0 = neg ? c : a; x2 = neg ? a : c;
                 bool neg2 = false;
-                Fr w2 = twiddle(tw, (j + m) << (p.log_n - s - 2), p.log_n, p.inverse, neg2);
+                Fr w2 = twiddle(tw, ((j + m) << (p.log_n - s - 2)) + (kbase >> (s + 2)), p.log_n, p.inverse, neg2);
                 x3 = x3 * w2;
                 Fr d = x1 + x3, e = x1 - x3;
                 x1 = neg2 ? e : d; x3 = neg2 ? d : e;
@@ -215,7 +238,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
         for (uint32_t e = tid; e < E; e += nthr) {
             uint32_t kj = e >> p.log_t, tl = e & (T - 1);
             Fr v = sm_ld(sm, SW(kj, tl), E);
-            uint64_t ex = ((uint64_t)kj * (p.low_offset + low0 + tl)) << p.tw_shift;
+            uint64_t ex = p.fold ? 0 : ((uint64_t)kj * (p.low_offset + low0 + tl)) << p.tw_shift;
             if (ex != 0) {
                 bool neg;
                 Fr w = twiddle(tw, (uint32_t)ex, p.log_n, p.inverse, neg);
@@ -250,12 +273,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
 // destination).  Used for the vanishing polynomial Z (m + 1 coefficients in a 2^20-point transform, batched.cu).
 __global__ void __launch_bounds__(256) ntt_sparse_first_pass_kernel(const Fr* __restrict__ in, Fr* __restrict__ out,
                                                                     const Fr* __restrict__ tw, uint32_t log_n, uint32_t log_r,
-                                                                    uint32_t nz, uint32_t inverse) {
+                                                                    uint32_t nz, uint32_t inverse, uint32_t fold) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t k = idx / nz, low = idx % nz;
     if (k >= (1u << log_r)) return;
     Fr v = ldg_fr(&in[low]);
-    const uint32_t ex = k * low;              // < 2^log_r * S = N: no wrap before the mask in twiddle()
+    const uint32_t ex = fold ? 0u : k * low;  // < 2^log_r * S = N: no wrap before the mask in twiddle(); folded plans
+                                              // leave the twiddle to the next pass: a plain broadcast
     if (ex != 0) {
         bool neg;
         Fr w = twiddle(tw, ex, log_n, inverse, neg);
@@ -311,6 +335,11 @@ int ntt_get_twiddles(uint32_t log_n, cudaStream_t stream, const Fr** out) {
 static uint32_t ntt_swizzle_enabled() {
     const char* e = getenv("KZGB_NTT_SWZ");
     return (e && *e == '1') ? 1u : 0u;
+}
+
+static uint32_t ntt_fold_enabled() {   // KZGB_NTT_FOLD=0: round-1 scheme (explicit inter-pass twiddle multiplication)
+    const char* e = getenv("KZGB_NTT_FOLD");
+    return (e && *e == '0') ? 0u : 1u;
 }
 
 struct NttPlan {
@@ -397,6 +426,7 @@ int ntt_columns_run(Fr* d_slab, uint32_t log_n, uint32_t log_n1, uint32_t log_c,
     p.apply_scale = 0;
     p.batch_stride = 0;
     p.swz = ntt_swizzle_enabled();
+    p.fold = 0;   // four-step column pass: the row pass that follows is a batch of PLAIN transforms, so the twiddle is applied here
     p.log_t = std::min<uint32_t>(NTT_MAX_TILE_LOG - p.log_r, log_c);
     size_t tiles = ((size_t)1 << log_c) >> p.log_t;
     size_t smem = (size_t)32 << (p.log_r + p.log_t);
@@ -461,6 +491,7 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
         p.tw_shift = log_n - p.log_nj;
         p.low_offset = 0;
         p.swz = ntt_swizzle_enabled();
+        p.fold = ntt_fold_enabled();
         p.batch_stride = (uint64_t)1 << log_n;
         bool last = (j == pl.npass - 1);
         p.apply_scale = (last && apply_scale) ? 1 : 0;
@@ -482,7 +513,7 @@ int ntt_run(Fr* d_data, Fr* d_tmp, uint32_t log_n, bool inverse, cudaStream_t st
             KZG_CUDA(cudaMemsetAsync(dst, 0, (size_t)32 << log_n, stream));
             const uint32_t work = nonzero_prefix << p.log_r;
             ntt_sparse_first_pass_kernel<<<div_up(work, 256), 256, 0, stream>>>(src, dst, tw, log_n, p.log_r, nonzero_prefix,
-                                                                                p.inverse);
+                                                                                p.inverse, p.fold);
             KZG_LAUNCHED();
             continue;
         }
