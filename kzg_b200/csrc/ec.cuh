@@ -162,7 +162,11 @@ KZG_DI void xyzz_add(XYZZ& acc, const XYZZ& q) {
     acc.zz = acc.zz * q.zz * PP;
     acc.zzz = acc.zzz * q.zzz * PPP;
     Fq X3 = R.sqr() - PPP - Q.dbl();
+#ifdef KZG_OUTLINE_FQ_MUL
+    acc.y = Fq::mul_sub_mul_fused_outlined(R, Q - X3, S1, PPP);   // one interleaved pass for both products (field.cuh)
+#else
     acc.y = R * (Q - X3) - S1 * PPP;
+#endif
     acc.x = X3;
 }
 

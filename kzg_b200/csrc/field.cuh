@@ -674,6 +674,94 @@ struct Fe {
         T[2 * N - 1] = addc(T[2 * N - 1], P::mod(N - 1) & borrow);
         return redc_wide(T);
     }
+    // (a*b + c*d) / R mod MOD in ONE interleaved Montgomery pass: every round adds the two product rows a*b_i and c*d_i
+    // and performs one reduction row -- 2*N^2 + N^2 + N wide multiply-adds instead of 2*(2*N^2 + N) for two products,
+    // with the carry-chain structure (and therefore the instruction mix) of mul_inline: no extra additions, one final
+    // subtraction instead of two.  Inputs a, b, d < MOD and c <= MOD (so that MOD - y can be passed for a subtraction):
+    // the running value stays below 3*MOD, which must fit the N-limb frame: 3*MOD < 2^(32N).  True for Fq (p < 2^381),
+    // FALSE for Fr (3r > 2^256) -- Fq only (static_assert below; the host model shows the Fr overflow).  The result
+    // (a*b + c*d + M*MOD)/R < MOD*(2*MOD/R + 1) < 1.25*MOD needs one final subtraction.
+    KZG_DI static void mul_row_acc(uint32_t* nE, uint32_t* nO, const uint32_t* a, uint32_t bi) {
+        nO[0] = mad_lo_cc(a[1], bi, nO[0]);
+        nO[1] = madc_hi_cc(a[1], bi, nO[1]);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+            nO[j] = madc_lo_cc(a[j + 1], bi, nO[j]);
+            nO[j + 1] = madc_hi_cc(a[j + 1], bi, nO[j + 1]);
+        }
+        nO[N - 2] = madc_lo_cc(a[N - 1], bi, nO[N - 2]);
+        nO[N - 1] = madc_hi(a[N - 1], bi, nO[N - 1]);
+        nE[0] = mad_lo_cc(a[0], bi, nE[0]);
+        nE[1] = madc_hi_cc(a[0], bi, nE[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+            nE[j] = madc_lo_cc(a[j], bi, nE[j]);
+            nE[j + 1] = madc_hi_cc(a[j], bi, nE[j + 1]);
+        }
+        nO[N - 1] = addc(nO[N - 1], 0);
+    }
+    KZG_DI static Fe mul_add_mul(const Fe& a, const Fe& b, const Fe& c, const Fe& d) {
+        static_assert(bits() + 2 <= 32 * N, "mul_add_mul: 3*MOD must fit in N limbs (Fq only)");
+        uint32_t E[N], O[N];
+        {   // round 0: the first row needs no accumulation
+            const uint32_t bi = b.l[0];
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                O[j] = mul_lo(a.l[j + 1], bi);
+                O[j + 1] = mul_hi(a.l[j + 1], bi);
+                E[j] = mul_lo(a.l[j], bi);
+                E[j + 1] = mul_hi(a.l[j], bi);
+            }
+            mul_row_acc(E, O, c.l, d.l[0]);
+            reduce_step(E, O);
+        }
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+            const uint32_t bi = b.l[i];
+            uint32_t nE[N], nO[N];
+#pragma unroll
+            for (int j = 0; j < N; j++) nE[j] = O[j];
+            nE[0] = add_cc(nE[0], E[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                nO[j] = madc_lo_cc(a.l[j + 1], bi, E[j + 2]);
+                nO[j + 1] = madc_hi_cc(a.l[j + 1], bi, E[j + 3]);
+            }
+            nO[N - 2] = madc_lo_cc(a.l[N - 1], bi, 0);
+            nO[N - 1] = madc_hi(a.l[N - 1], bi, 0);
+            nE[0] = mad_lo_cc(a.l[0], bi, nE[0]);
+            nE[1] = madc_hi_cc(a.l[0], bi, nE[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                nE[j] = madc_lo_cc(a.l[j], bi, nE[j]);
+                nE[j + 1] = madc_hi_cc(a.l[j], bi, nE[j + 1]);
+            }
+            nO[N - 1] = addc(nO[N - 1], 0);
+            mul_row_acc(nE, nO, c.l, d.l[i]);
+            reduce_step(nE, nO);
+#pragma unroll
+            for (int j = 0; j < N; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+        }
+        Fe r;
+        r.l[0] = add_cc(E[1], O[0]);
+#pragma unroll
+        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(E[j + 1], O[j]);
+        r.l[N - 1] = addc(0, O[N - 1]);
+        r.final_sub();
+        return r;
+    }
+    // MOD - a without the "a == 0" special case: a value in (0, MOD], acceptable as the `c` operand of mul_add_mul
+    KZG_DI Fe neg_raw() const {
+        Fe r;
+        r.l[0] = sub_cc(P::mod(0), l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(P::mod(i), l[i]);
+        r.l[N - 1] = subc(P::mod(N - 1), l[N - 1]);
+        return r;
+    }
+    // a*b - c*d
+    KZG_DI static Fe mul_sub_mul_fused(const Fe& a, const Fe& b, const Fe& c, const Fe& d) { return mul_add_mul(a, b, c.neg_raw(), d); }
+    __device__ __noinline__ static Fe mul_sub_mul_fused_outlined(Fe a, Fe b, Fe c, Fe d) { return mul_add_mul(a, b, c.neg_raw(), d); }
     __device__ __noinline__ static Fe mul_kara_outlined(Fe a, Fe b) { return mul_kara(a, b); }
     __device__ __noinline__ static Fe mul_sub_mul_outlined(Fe a, Fe b, Fe c, Fe d) { return mul_sub_mul(a, b, c, d); }
 

@@ -109,10 +109,14 @@ static int run(const char* name, int iters) {
         F r1 = F::mul_kara(a, b);
         F r2 = F::mul_sub_mul(a, b, c, d);
         F r3 = F::sqr_inline(a);
+        F r4;                                        // one interleaved pass for a*b + (MOD - c)*d: Fq only (3*MOD must fit)
+        if constexpr (P::N == 12) r4 = F::mul_sub_mul_fused(a, b, c, d);
+        else memcpy(r4.l, df, 8 * W);
         if (memcmp(r0.l, ab, 8 * W)) { printf("%s: mul_inline mismatch at %d\n", name, it); bad++; }
         if (memcmp(r1.l, ab, 8 * W)) { printf("%s: mul_kara mismatch at %d\n", name, it); bad++; }
         if (memcmp(r2.l, df, 8 * W)) { printf("%s: mul_sub_mul mismatch at %d\n", name, it); bad++; }
         if (memcmp(r3.l, aa, 8 * W)) { printf("%s: sqr_inline mismatch at %d\n", name, it); bad++; }
+        if (memcmp(r4.l, df, 8 * W)) { printf("%s: mul_sub_mul_fused mismatch at %d\n", name, it); bad++; }
     }
     printf("%s: %d iterations, %d mismatches\n", name, iters, bad);
     return bad;
