@@ -292,6 +292,10 @@ struct Fe {
 #endif
         return mul_inline(a, b);
     }
+    // FINAL = false: "lazy" form for operands and results in [0, 2*MOD) instead of [0, MOD): the conditional final
+    // subtraction is skipped.  Valid where 4*MOD < 2^(32N) (Fq: p < 2^381): inputs < 2*MOD give (a*b + M*MOD)/R <
+    // MOD*(4*MOD/R + 1) < 1.5*MOD, and the running value stays below 3*MOD.  See the *_lazy helpers below.
+    template <bool FINAL = true>
     KZG_DI static Fe mul_inline(const Fe& a, const Fe& b) {
         uint32_t E[N], O[N];
         // ---- i = 0: plain products, no accumulation ----
@@ -340,7 +344,7 @@ struct Fe {
 #pragma unroll
         for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(E[j + 1], O[j]);
         r.l[N - 1] = addc(0, O[N - 1]);
-        r.final_sub();
+        if constexpr (FINAL) r.final_sub();
         return r;
     }
 
@@ -449,6 +453,7 @@ struct Fe {
 
     // a^2/R mod MOD with N(N+1)/2 partial products for the square (off-diagonal terms once, doubled, plus the
     // diagonal) followed by a word-serial Montgomery reduction: 78 + 144 wide multiply-adds for Fq instead of 288.
+    template <bool FINAL = true>
     KZG_DI static Fe sqr_inline(const Fe& a) {
         constexpr int M = 2 * N;
         // off-diagonal products a_i*a_j (i < j) in two accumulators by parity of i+j:
@@ -506,7 +511,7 @@ struct Fe {
             if (i < N - 1) T[2 * i + 1] = madc_hi_cc(a.l[i], a.l[i], T[2 * i + 1]);
             else T[2 * i + 1] = madc_hi(a.l[i], a.l[i], T[2 * i + 1]);
         }
-        return redc_wide(T);
+        return redc_wide<FINAL>(T);
     }
 
     // ------------------------------------------------------------------------------------------------------
@@ -611,6 +616,7 @@ struct Fe {
     // T (2N limbs, < MOD * 2^(32N)) -> T / 2^(32N) mod MOD.  Only the low N limbs take part in the N word-serial rounds
     // ((T + M*MOD)/R = (T_lo + M*MOD)/R + T_hi exactly); they run on the interleaved (E, O) frame of mul_inline, where
     // the carry of the frame shift enters the next round's odd chain, so no round pays a carry ripple.
+    template <bool FINAL = true>
     KZG_DI static Fe redc_wide(const uint32_t* T) {
         uint32_t E[N], O[N];
 #pragma unroll
@@ -651,7 +657,7 @@ struct Fe {
 #pragma unroll
         for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(r.l[j], T[N + j]);
         r.l[N - 1] = addc(r.l[N - 1], T[2 * N - 1]);
-        r.final_sub();
+        if constexpr (FINAL) r.final_sub();
         return r;
     }
     KZG_DI static Fe mul_kara(const Fe& a, const Fe& b) {
@@ -700,6 +706,7 @@ struct Fe {
         }
         nO[N - 1] = addc(nO[N - 1], 0);
     }
+    template <bool FINAL = true>
     KZG_DI static Fe mul_add_mul(const Fe& a, const Fe& b, const Fe& c, const Fe& d) {
         static_assert(bits() + 2 <= 32 * N, "mul_add_mul: 3*MOD must fit in N limbs (Fq only)");
         uint32_t E[N], O[N];
@@ -747,7 +754,7 @@ struct Fe {
 #pragma unroll
         for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(E[j + 1], O[j]);
         r.l[N - 1] = addc(0, O[N - 1]);
-        r.final_sub();
+        if constexpr (FINAL) r.final_sub();
         return r;
     }
     // MOD - a without the "a == 0" special case: a value in (0, MOD], acceptable as the `c` operand of mul_add_mul
@@ -759,6 +766,59 @@ struct Fe {
         r.l[N - 1] = subc(P::mod(N - 1), l[N - 1]);
         return r;
     }
+    // ---- lazy range [0, 2*MOD) (Fq only: needs 8*MOD < 2^(32N)) -------------------------------------------------
+    // The accumulate kernel keeps its running XYZZ sum in this range: the nine products of a mixed addition skip their
+    // final subtraction, differences add 2*MOD instead of MOD, and only zero tests and stores look at canonical values.
+    __host__ __device__ static constexpr uint32_t mod2(int i) {   // limb i of 2*MOD
+        return (P::mod(i) << 1) | (i > 0 ? (P::mod(i - 1) >> 31) : 0u);
+    }
+    KZG_DI static Fe sub_lazy(const Fe& a, const Fe& b) {         // a - b (+ 2*MOD when negative), inputs and result < 2*MOD
+        Fe r;
+        r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+        const uint32_t borrow = subc(0, 0);
+        r.l[0] = add_cc(r.l[0], mod2(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], mod2(i) & borrow);
+        r.l[N - 1] = addc(r.l[N - 1], mod2(N - 1) & borrow);
+        return r;
+    }
+    KZG_DI Fe dbl_lazy() const {                                   // 2a reduced below 2*MOD (a < 2*MOD)
+        Fe r;
+        r.l[0] = add_cc(l[0], l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(l[i], l[i]);
+        r.l[N - 1] = addc(l[N - 1], l[N - 1]);
+        uint32_t t[N];
+        t[0] = sub_cc(r.l[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) t[i] = subc_cc(r.l[i], mod2(i));
+        const uint32_t borrow = subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = borrow ? r.l[i] : t[i];
+        return r;
+    }
+    KZG_DI Fe neg_lazy() const {                                   // 2*MOD - a, in (0, 2*MOD] for a < 2*MOD
+        Fe r;
+        r.l[0] = sub_cc(mod2(0), l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(mod2(i), l[i]);
+        r.l[N - 1] = subc(mod2(N - 1), l[N - 1]);
+        return r;
+    }
+    KZG_DI bool is_zero_modp() const {                             // a in {0, MOD} (a < 2*MOD)
+        uint32_t z = 0, m = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) { z |= l[i]; m |= l[i] ^ P::mod(i); }
+        return z == 0 || m == 0;
+    }
+    KZG_DI Fe canon() const { Fe r = *this; r.final_sub(); return r; }
+    __device__ __noinline__ static Fe mul_lazy_outlined(Fe a, Fe b) { return mul_inline<false>(a, b); }
+    __device__ __noinline__ static Fe sqr_lazy_outlined(Fe a) { return sqr_inline<false>(a); }
+    // a*b + c*d with c already negated by the caller (neg_lazy): result < 2*MOD, no final subtraction
+    __device__ __noinline__ static Fe mul_add_mul_lazy_outlined(Fe a, Fe b, Fe c, Fe d) { return mul_add_mul<false>(a, b, c, d); }
+
     // a*b - c*d
     KZG_DI static Fe mul_sub_mul_fused(const Fe& a, const Fe& b, const Fe& c, const Fe& d) { return mul_add_mul(a, b, c.neg_raw(), d); }
     __device__ __noinline__ static Fe mul_sub_mul_fused_outlined(Fe a, Fe b, Fe c, Fe d) { return mul_add_mul(a, b, c.neg_raw(), d); }

@@ -118,6 +118,54 @@ static int run(const char* name, int iters) {
         if (memcmp(r3.l, aa, 8 * W)) { printf("%s: sqr_inline mismatch at %d\n", name, it); bad++; }
         if (memcmp(r4.l, df, 8 * W)) { printf("%s: mul_sub_mul_fused mismatch at %d\n", name, it); bad++; }
     }
+    // ---- lazy range [0, 2*MOD) (Fq only): operands are canonical values with MOD added at random; every lazy routine
+    // must return a value below 2*MOD that is congruent to the model's canonical result
+    if constexpr (P::N == 12) {
+        uint64_t m[W];
+        Model<P>::mod64(m);
+        auto lift = [&](F x) {   // x or x + MOD
+            if (rnd() & 1) {
+                u128 c = 0;
+                uint64_t v[W];
+                memcpy(v, x.l, 8 * W);
+                for (int i = 0; i < W; i++) { c += (u128)v[i] + m[i]; v[i] = (uint64_t)c; c >>= 64; }
+                memcpy(x.l, v, 8 * W);
+            }
+            return x;
+        };
+        auto below_2p = [&](const F& x) {
+            uint64_t v[W], two[W];
+            memcpy(v, x.l, 8 * W);
+            u128 c = 0;
+            for (int i = 0; i < W; i++) { c += (u128)m[i] + m[i]; two[i] = (uint64_t)c; c >>= 64; }
+            return !Model<P>::geq(v, two);
+        };
+        for (int it = 0; it < iters && bad < 5; it++) {
+            F a, b, c, d;
+            random_fe<P>(a, it < 64 ? it % 6 : 0); random_fe<P>(b, it < 64 ? (it / 6) % 6 : 0); random_fe<P>(c, 0); random_fe<P>(d, 0);
+            uint64_t ma[W], mb[W], mc[W], md[W], ab[W], cd[W], df[W], aa[W], amb[W], a2[W], zero[W] = {0};
+            memcpy(ma, a.l, 8 * W); memcpy(mb, b.l, 8 * W); memcpy(mc, c.l, 8 * W); memcpy(md, d.l, 8 * W);
+            Model<P>::mul(ab, ma, mb); Model<P>::mul(cd, mc, md); Model<P>::mul(aa, ma, ma);
+            Model<P>::submod(df, ab, cd); Model<P>::submod(amb, ma, mb);
+            uint64_t na[W];
+            Model<P>::submod(na, zero, ma); Model<P>::submod(a2, ma, na);          // a - (-a) = 2a
+            F la = lift(a), lb = lift(b), lc = lift(c), ld = lift(d);
+            F r1 = F::template mul_inline<false>(la, lb);
+            F r2 = F::template sqr_inline<false>(la);
+            F r3 = F::template mul_add_mul<false>(la, lb, lc.neg_lazy(), ld);
+            F r4 = F::sub_lazy(la, lb);
+            F r5 = la.dbl_lazy();
+            struct { const char* n; F v; uint64_t* want; } chk[5] = {{"mul_lazy", r1, ab}, {"sqr_lazy", r2, aa}, {"fused_lazy", r3, df},
+                                                                   {"sub_lazy", r4, amb}, {"dbl_lazy", r5, a2}};
+            for (auto& k : chk) {
+                F cv = k.v.canon();
+                if (!below_2p(k.v) || memcmp(cv.l, k.want, 8 * W)) { printf("%s: %s mismatch at %d\n", name, k.n, it); bad++; }
+            }
+            F z = F::sub_lazy(la, la), pm;
+            memcpy(pm.l, m, 8 * W);
+            if (!z.is_zero_modp() || !pm.is_zero_modp() || (!a.is_zero() && la.is_zero_modp())) { printf("%s: is_zero_modp at %d\n", name, it); bad++; }
+        }
+    }
     printf("%s: %d iterations, %d mismatches\n", name, iters, bad);
     return bad;
 }
