@@ -243,3 +243,37 @@ def test_batched_witness_beyond_4096_points(gpu, cpu):
     ys[17] = scalar.fr(3)
     assert gpu.witness_batched(srs, p, xs, ys)[0] == gpu.KZGB_POINT_NOT_ON_POLYNOMIAL
     srs.close()
+
+
+def test_shutdown_releases_handles_and_allows_reinit():
+    """kzgb_shutdown with live handles (own process): their device memory is released, a later destroy only frees the
+    host side, and a re-initialised library works again (per-device kernel attributes and caches are rebuilt)."""
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from kzg_b200 import _ffi
+from oracle import cpu
+cpu.build()
+_ffi.init(0)
+s = cpu.fr_stream(69, 1)[0]
+p = cpu.fr_stream(42, 2048)
+srs = _ffi.srs_generate(0, s, 2048)
+want_c = srs.msm(p)
+want_f = _ffi.ntt(p, 11, False)[1]
+h = _ffi.DevicePoly(p)
+lib = _ffi.load()
+assert lib.kzgb_shutdown() == 0
+import ctypes
+assert lib.kzgb_ntt_fr(ctypes.c_void_p(p.ctypes.data), ctypes.c_uint32(11), ctypes.c_int(0)) < 0   # not initialised: loud failure
+assert lib.kzgb_srs_destroy(srs._h) == 0                    # handle outlived the shutdown: host side only
+srs._h = None
+h._h = None                                                  # (its buffers went with the shutdown's cache / context)
+assert lib.kzgb_init(0) == 0
+srs2 = _ffi.srs_generate(0, s, 2048)
+assert (srs2.msm(p) == want_c).all()
+assert (_ffi.ntt(p, 11, False)[1] == want_f).all()
+print("REINIT_OK")
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "REINIT_OK" in r.stdout, r.stdout + r.stderr
