@@ -364,6 +364,15 @@ def bench_single(args, env):
                             "Karatsuba product with 12 % fewer IMAD.WIDE and ~150 more ALU ops is 11 % slower): see DESIGN.md")
 
     def secondary():
+        # ---- the same host-pointer call from ordinary pageable memory (what a Rust Vec<Fr> is): upload_async's relay ----
+        pageable = [hp.numpy().view(np.uint64).copy() for hp in host_polys]
+
+        def pageable_step(i):
+            _ffi.check(lib.kzgb_msm_g1(srs._h, _ffi.ptr(pageable[i % 2]), C.c_size_t(N_POINTS), _ffi.ptr(out_host)))
+        pg_ms = T.wall(pageable_step, K, warmup=3)
+        extra["e2e_pageable_host"] = {"ms_per_step": pg_ms, "value": N_POINTS / (pg_ms * 1e-3),
+                                      "note": "kzgb_msm_g1 from unpinned numpy memory: 32 MiB relayed through the lane's pinned ring "
+                                              "by 4 host threads (KZGB_UPLOAD_THREADS); profiles/r02s_pageable_upload_relay.log"}
         # ---- pipelined batch entry points (NOT the headline): K commits per call ----
         d_out = torch.zeros((K, 12), dtype=torch.int64, device=dev)
 

@@ -1,5 +1,7 @@
 // api_core.cu -- lifecycle, error reporting, scratch/pinned arenas.
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -151,6 +153,126 @@ void* pinned_reserve(size_t bytes) {
     }
     c.pinned_bytes = bytes;
     return c.pinned;
+}
+
+// ---- host -> device upload with a pinned relay for pageable sources ----
+namespace {
+constexpr size_t RELAY_SLICE = size_t(2) << 20;   // bytes per pinned slice
+constexpr int RELAY_MAX_THREADS = 8;              // 2 slices per thread
+constexpr size_t RELAY_MIN_BYTES = size_t(4) << 20;
+
+int relay_threads() {
+    static int n = [] {
+        const char* e = getenv("KZGB_UPLOAD_THREADS");   // 0 = leave pageable copies to the driver
+        int v = e ? atoi(e) : 4;
+        return v < 0 ? 0 : (v > RELAY_MAX_THREADS ? RELAY_MAX_THREADS : v);
+    }();
+    return n;
+}
+
+bool host_is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+}  // namespace
+
+cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    const int T = relay_threads();
+    if (bytes < RELAY_MIN_BYTES || T == 0 || !host_is_pageable(src))
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    Lane& l = lane();
+    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE);
+    if (!ring) return cudaErrorMemoryAllocation;
+    for (int i = 0; i < 2 * T; i++)
+        if (!l.relay_ev[i]) {
+            cudaError_t e = cudaEventCreateWithFlags(&l.relay_ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+    const size_t slices = (bytes + RELAY_SLICE - 1) / RELAY_SLICE;
+    const int device = ctx().device;
+    cudaError_t errs[RELAY_MAX_THREADS];
+    // worker t relays slices t, t+T, t+2T, ... through its own two pinned slots
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        size_t j = 0;
+        for (size_t k = t; k < slices && e == cudaSuccess; k += T, j++) {
+            const int slot = 2 * t + int(j & 1);
+            char* buf = ring + size_t(slot) * RELAY_SLICE;
+            const size_t off = k * RELAY_SLICE, len = bytes - off < RELAY_SLICE ? bytes - off : RELAY_SLICE;
+            e = cudaEventSynchronize(l.relay_ev[slot]);   // the slot's previous transfer (this call's or an earlier one's) has left
+            if (e != cudaSuccess) break;
+            memcpy(buf, (const char*)src + off, len);
+            e = cudaMemcpyAsync((char*)dst + off, buf, len, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(l.relay_ev[slot], st);
+        }
+        errs[t] = e;
+    };
+    std::thread th[RELAY_MAX_THREADS];
+    for (int t = 1; t < T; t++) th[t] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < T; t++) th[t].join();
+    for (int t = 0; t < T; t++)
+        if (errs[t] != cudaSuccess) return errs[t];
+    return cudaSuccess;   // the source has been read; the last slices may still be in flight on `st`
+}
+
+// Device -> host counterpart: pinned destinations get a plain cudaMemcpyAsync (the caller synchronises `st` as before);
+// large pageable ones are filled through the same ring, each worker keeping one slice in flight while it copies the
+// previous one out.  On return from the relayed path the destination is complete.
+cudaError_t download_async(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+    const int T = relay_threads();
+    if (bytes < RELAY_MIN_BYTES || T == 0 || !host_is_pageable(dst))
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    Lane& l = lane();
+    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE);
+    if (!ring) return cudaErrorMemoryAllocation;
+    for (int i = 0; i < 2 * T; i++)
+        if (!l.relay_ev[i]) {
+            cudaError_t e = cudaEventCreateWithFlags(&l.relay_ev[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+    const size_t slices = (bytes + RELAY_SLICE - 1) / RELAY_SLICE;
+    const int device = ctx().device;
+    cudaError_t errs[RELAY_MAX_THREADS];
+    auto work = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        auto span = [&](size_t k, size_t* off, size_t* len) {
+            *off = k * RELAY_SLICE;
+            *len = bytes - *off < RELAY_SLICE ? bytes - *off : RELAY_SLICE;
+        };
+        auto fetch = [&](size_t k, int slot) {   // device -> ring slot, ordered on st
+            size_t off, len;
+            span(k, &off, &len);
+            cudaError_t f = cudaEventSynchronize(l.relay_ev[slot]);   // an earlier upload may still be reading the slot
+            if (f == cudaSuccess) f = cudaMemcpyAsync(ring + size_t(slot) * RELAY_SLICE, (const char*)src + off, len, cudaMemcpyDeviceToHost, st);
+            if (f == cudaSuccess) f = cudaEventRecord(l.relay_ev[slot], st);
+            return f;
+        };
+        size_t j = 0;
+        if (e == cudaSuccess && size_t(t) < slices) e = fetch(t, 2 * t);
+        for (size_t k = t; k < slices && e == cudaSuccess; k += T, j++) {
+            const int slot = 2 * t + int(j & 1);
+            if (k + T < slices) e = fetch(k + T, 2 * t + int((j + 1) & 1));
+            if (e != cudaSuccess) break;
+            e = cudaEventSynchronize(l.relay_ev[slot]);
+            if (e != cudaSuccess) break;
+            size_t off, len;
+            span(k, &off, &len);
+            memcpy((char*)dst + off, ring + size_t(slot) * RELAY_SLICE, len);
+        }
+        errs[t] = e;
+    };
+    std::thread th[RELAY_MAX_THREADS];
+    for (int t = 1; t < T; t++) th[t] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < T; t++) th[t].join();
+    for (int t = 0; t < T; t++)
+        if (errs[t] != cudaSuccess) return errs[t];
+    return cudaSuccess;
 }
 
 // ---- stage timer ----
@@ -337,6 +459,8 @@ int kzgb_shutdown(void) {
         if (l.side) cudaStreamDestroy(l.side);
         if (l.fork_ev) cudaEventDestroy(l.fork_ev);
         if (l.join_ev) cudaEventDestroy(l.join_ev);
+        for (cudaEvent_t e : l.relay_ev)
+            if (e) cudaEventDestroy(e);
         l = Lane();
     }
     c.initialised = false;

@@ -85,7 +85,7 @@ KZGB_API int kzgb_poly_upload(const kzgb_fr* coeffs, size_t n, kzgb_poly** out) 
     kzgb_poly* p = new kzgb_poly();
     p->n = n;
     cudaError_t e = poly_alloc((void**)&p->d_data, n * sizeof(Fr), &p->data_cap);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_data, coeffs, n * sizeof(Fr), cudaMemcpyHostToDevice, lane().stream);
+    if (e == cudaSuccess) e = upload_async(p->d_data, coeffs, n * sizeof(Fr), lane().stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(lane().stream);
     if (e != cudaSuccess) {
         if (p->d_data) cudaFree(p->d_data);
@@ -118,7 +118,7 @@ KZGB_API int kzgb_poly_download(kzgb_poly* p, kzgb_fr* out) {
     if (!p || !out) { set_error("kzgb_poly_download: null argument"); return KZGB_ERR_INVALID_ARG; }
     KZG_LOCK_POLY(p);
     cudaStream_t st = use_stream(lane().stream);
-    KZG_CUDA(cudaMemcpyAsync(out, p->d_data, p->n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    KZG_CUDA(download_async(out, p->d_data, p->n * sizeof(Fr), st));
     KZG_CUDA(cudaStreamSynchronize(st));
     return KZGB_OK;
 }

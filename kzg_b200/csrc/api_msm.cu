@@ -123,7 +123,7 @@ static int msm_host(kzgb_srs* s, const kzgb_fr* scalars, size_t m, void* out, in
     size_t bytes = m * sizeof(kzgb_fr);
     char* d = (char*)staging_reserve(bytes + 256);
     if (!d) return KZGB_ERR_CUDA;
-    if (m) KZG_CUDA(cudaMemcpyAsync(d + 256, scalars, bytes, cudaMemcpyHostToDevice, lane().stream));
+    if (m) KZG_CUDA(upload_async(d + 256, scalars, bytes, lane().stream));
     const XYZZ* res = nullptr;
     int rc = msm_run(s, d + 256, m, lane().stream, &res);
     if (rc) return rc;
@@ -212,7 +212,7 @@ int msm_batch_run(kzgb_srs* s, MsmPipe& g_pipe, const void* const* scalars, cons
             }
             // the staging buffer of this slot is free once the tail of item i-2 has finished
             if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(g_pipe.copy, g_pipe.done[k], 0));
-            if (m) KZG_CUDA(cudaMemcpyAsync(g_pipe.d_stage[k], scalars[i], bytes, cudaMemcpyHostToDevice, g_pipe.copy));
+            if (m) KZG_CUDA(upload_async(g_pipe.d_stage[k], scalars[i], bytes, g_pipe.copy));
             KZG_CUDA(cudaEventRecord(g_pipe.staged[k], g_pipe.copy));
             KZG_CUDA(cudaStreamWaitEvent(g_pipe.heavy, g_pipe.staged[k], 0));
             d_sc = g_pipe.d_stage[k];
@@ -433,7 +433,7 @@ KZGB_API int kzgb_witness_coeff_many(kzgb_srs* s, const kzgb_fr* p, size_t n, co
     int* d_flag = (int*)(buf + pb + xyb + rb);
     if ((rc = pipe_reserve_results(g_pipe, m)) || (rc = pipe_reserve_stage(g_pipe, qn * 32))) return rc;
     cudaStream_t hs = g_pipe.heavy;
-    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, hs));
+    KZG_CUDA(upload_async(d_p, p, n * 32, hs));
     // interleave (x_i, y_i) on the device side: two strided copies
     KZG_CUDA(cudaMemcpy2DAsync(d_xy, 64, xs, 32, 32, m, cudaMemcpyHostToDevice, hs));
     KZG_CUDA(cudaMemcpy2DAsync(d_xy + 1, 64, ys, 32, 32, m, cudaMemcpyHostToDevice, hs));
@@ -489,7 +489,7 @@ KZGB_API int kzgb_witness_eval_many(kzgb_srs* lagrange_srs, const kzgb_fr* evals
     if (!ws) return KZGB_ERR_CUDA;
     if ((rc = pipe_reserve_results(g_pipe, m)) || (rc = pipe_reserve_stage(g_pipe, d * 32))) return rc;
     cudaStream_t hs = g_pipe.heavy;
-    KZG_CUDA(cudaMemcpyAsync(d_evals, evals, d * 32, cudaMemcpyHostToDevice, hs));
+    KZG_CUDA(upload_async(d_evals, evals, d * 32, hs));
     for (size_t j = 0; j < m && rc == KZGB_OK; j++) {
         const int k = (int)(j & 1);
         if (g_pipe.used[k]) KZG_CUDA(cudaStreamWaitEvent(hs, g_pipe.done[k], 0));

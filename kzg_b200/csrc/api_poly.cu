@@ -34,12 +34,12 @@ KZGB_API int kzgb_divide_linear(const kzgb_fr* p, size_t n, const kzgb_fr* x, co
     Fr* d_x = (Fr*)(d + 2 * pb + ws);
     Fr* d_y = d_x + 1;
     Fr* d_rem = d_x + 2;
-    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d_p, p, n * 32, lane().stream));
     KZG_CUDA(cudaMemcpyAsync(d_x, x, 32, cudaMemcpyHostToDevice, lane().stream));
     if (y) KZG_CUDA(cudaMemcpyAsync(d_y, y, 32, cudaMemcpyHostToDevice, lane().stream));
     int st = scan_divide_linear(d_p, n, d_x, y ? d_y : nullptr, d_q, d_rem, d_ws, lane().stream);
     if (st) return st;
-    if (n > 1) KZG_CUDA(cudaMemcpyAsync(q_out, d_q, (n - 1) * 32, cudaMemcpyDeviceToHost, lane().stream));
+    if (n > 1) KZG_CUDA(download_async(q_out, d_q, (n - 1) * 32, lane().stream));
     KZG_CUDA(cudaMemcpyAsync(rem_out, d_rem, 32, cudaMemcpyDeviceToHost, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
@@ -122,7 +122,7 @@ KZGB_API int kzgb_witness_coeff(kzgb_srs* srs, const kzgb_fr* p, size_t n, const
     int rc = KZGB_OK;
     cudaError_t e;
     do {
-        if ((e = cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, lane().stream)) != cudaSuccess ||
+        if ((e = upload_async(d_p, p, n * 32, lane().stream)) != cudaSuccess ||
             (e = cudaMemcpyAsync(d_xy, x, 32, cudaMemcpyHostToDevice, lane().stream)) != cudaSuccess ||
             (e = cudaMemcpyAsync(d_xy + 1, y, 32, cudaMemcpyHostToDevice, lane().stream)) != cudaSuccess) {
             rc = cuda_fail(e, "H2D witness inputs", __FILE__, __LINE__);
@@ -148,10 +148,10 @@ KZGB_API int kzgb_div_by_omega_i(const kzgb_fr* evals, uint32_t log_d, size_t i,
     size_t pb = al256(d * 32);
     char* buf = (char*)scratch_reserve(2 * pb + al256(div_by_omega_workspace_bytes(log_d)));
     if (!buf) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(buf, evals, d * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(buf, evals, d * 32, lane().stream));
     int rc = div_by_omega_run((const Fr*)buf, log_d, (uint32_t)i, (Fr*)(buf + pb), buf + 2 * pb, lane().stream);
     if (rc) return rc;
-    KZG_CUDA(cudaMemcpyAsync(q_out, buf + pb, d * 32, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(q_out, buf + pb, d * 32, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
@@ -196,7 +196,7 @@ KZGB_API int kzgb_witness_eval(kzgb_srs* lagrange_srs, const kzgb_fr* evals, uin
     char* buf = (char*)staging_reserve(2 * pb + 256);
     if (!buf) return KZGB_ERR_CUDA;
     int rc;
-    cudaError_t e = cudaMemcpyAsync(buf, evals, d * 32, cudaMemcpyHostToDevice, lane().stream);
+    cudaError_t e = upload_async(buf, evals, d * 32, lane().stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "H2D evals", __FILE__, __LINE__);
     else rc = kzgb_witness_eval_dev(lagrange_srs, buf, log_d, i, buf + pb, buf + 2 * pb, lane().stream);
     if (rc == KZGB_OK) {

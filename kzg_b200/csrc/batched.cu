@@ -523,7 +523,7 @@ KZGB_API int kzgb_witness_batched(kzgb_srs* srs, const kzgb_fr* p, size_t n, con
     Fr* d_ys = (Fr*)(d + pb + mb);
     Fr* d_r = (Fr*)(d + pb + 2 * mb);
     char* d_out = d + pb + 2 * mb + rb;
-    KZG_CUDA(cudaMemcpyAsync(d_p, p, n * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d_p, p, n * 32, lane().stream));
     KZG_CUDA(cudaMemcpyAsync(d_xs, xs, m * 32, cudaMemcpyHostToDevice, lane().stream));
     KZG_CUDA(cudaMemcpyAsync(d_ys, ys, m * 32, cudaMemcpyHostToDevice, lane().stream));
     int rc = kzgb_witness_batched_dev(srs, d_p, n, d_xs, d_ys, m, d_r, d_out, lane().stream);

@@ -290,7 +290,7 @@ KZGB_API int kzgb_msm_g1_sharded(kzgb_srs* shard, const kzgb_fr* scalars, size_t
     const size_t bytes = m * sizeof(kzgb_fr);
     char* d = (char*)staging_reserve(bytes + 256);
     if (!d) return KZGB_ERR_CUDA;
-    if (m) KZG_CUDA(cudaMemcpyAsync(d + 256, scalars, bytes, cudaMemcpyHostToDevice, st));
+    if (m) KZG_CUDA(upload_async(d + 256, scalars, bytes, st));
     int rc = kzgb_msm_g1_sharded_dev(shard, d + 256, m, d, 0, st);
     if (rc) return rc;
     KZG_CUDA(cudaMemcpyAsync(out, d, sizeof(kzgb_p1_affine), cudaMemcpyDeviceToHost, st));

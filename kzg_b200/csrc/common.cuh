@@ -30,6 +30,8 @@ struct Lane {
     // fork/join inside one call (independent sub-chains of a pipeline run beside each other, see batched.cu)
     cudaStream_t side = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    // relay ring of upload_async (pageable host inputs): one event per pinned slice, created on first use
+    cudaEvent_t relay_ev[16] = {nullptr};
 };
 constexpr int KZG_MAX_LANES = 4;
 
@@ -72,6 +74,14 @@ int lane_side_stream(cudaStream_t* side, cudaEvent_t* fork_ev, cudaEvent_t* join
 void* scratch_reserve(size_t bytes);   // returns device pointer or nullptr (error set)
 void* staging_reserve(size_t bytes);   // device staging for host-pointer entry points
 void* pinned_reserve(size_t bytes);    // returns pinned host pointer or nullptr (error set)
+// Host -> device copy of a (possibly pageable) caller buffer, ordered on `st`.  Pinned or registered sources go
+// straight to cudaMemcpyAsync; large pageable ones (what a Rust Vec<Fr> is) are relayed through the lane's pinned ring
+// by a few host threads, so the PCIe transfer of one slice overlaps the host memcpy of the next ones.  Like a pageable
+// cudaMemcpyAsync it returns once the source has been read.
+cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// Device -> host: plain cudaMemcpyAsync for pinned destinations (synchronise `st` before reading), the threaded relay
+// for large pageable ones (complete on return).
+cudaError_t download_async(void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 #define KZG_CUDA(expr)                                                              \
     do {                                                                            \

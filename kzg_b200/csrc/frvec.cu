@@ -115,13 +115,13 @@ KZGB_API int kzgb_fr_vec_op(int op, kzgb_fr* a, const kzgb_fr* b, size_t n, cons
     size_t bytes = n * 32, pb = (bytes + 255) & ~(size_t)255;
     char* d = (char*)staging_reserve(2 * pb);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, a, bytes, cudaMemcpyHostToDevice, lane().stream));
-    if (op == 0 || op == 1) KZG_CUDA(cudaMemcpyAsync(d + pb, b, bytes, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d, a, bytes, lane().stream));
+    if (op == 0 || op == 1) KZG_CUDA(upload_async(d + pb, b, bytes, lane().stream));
     Fr kk = Fr::zero_host();
     if (k) memcpy(kk.l, k->l, 32);
     int st = fr_vec_op_run(op, (Fr*)d, (const Fr*)(d + pb), n, kk, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(a, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(a, d, bytes, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
@@ -138,10 +138,10 @@ KZGB_API int kzgb_coset_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
     size_t bytes = (size_t)32 << log_n;
     char* d = (char*)staging_reserve(2 * bytes);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d, inout, bytes, lane().stream));
     int st = coset_ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(inout, d, bytes, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }
@@ -170,14 +170,14 @@ KZGB_API int kzgb_poly_mul(const kzgb_fr* a, size_t na, const kzgb_fr* b, size_t
     Fr* db = (Fr*)(d + bytes);
     Fr* tmp = (Fr*)(d + 2 * bytes);
     KZG_CUDA(cudaMemsetAsync(d, 0, 2 * bytes, lane().stream));
-    KZG_CUDA(cudaMemcpyAsync(da, a, na * 32, cudaMemcpyHostToDevice, lane().stream));
-    KZG_CUDA(cudaMemcpyAsync(db, b, nb * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(da, a, na * 32, lane().stream));
+    KZG_CUDA(upload_async(db, b, nb * 32, lane().stream));
     int st;
     if ((st = ntt_run(da, tmp, log_m, false, lane().stream))) return st;
     if ((st = ntt_run(db, tmp, log_m, false, lane().stream))) return st;
     if ((st = fr_vec_op_run(0, da, db, m, Fr::zero_host(), lane().stream))) return st;
     if ((st = ntt_run(da, tmp, log_m, true, lane().stream))) return st;
-    KZG_CUDA(cudaMemcpyAsync(out, da, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(out, da, bytes, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     *m_out = m;
     return KZGB_OK;

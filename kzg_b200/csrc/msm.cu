@@ -884,8 +884,9 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     size_t wave = (size_t)c.sm_count * KZG_MSM_ACC_BLOCKS * 128;
     // entries per accumulate thread: 48 (five waves at 2^20 x 13 windows) balances the accumulate kernel best; from ~2^21
     // points on, the boundary partials (two per thread) make the fix-up the larger term and longer chunks win
-    // (2^21: 12.08 ms at 80 vs 12.25 ms at 48; profiles/r02e_msm_tail_knobs.log)
-    size_t target_chunk = p.total > ((size_t)1 << 24) ? 80 : 48;
+    // (2^21 points: 11.14 ms at 96 vs 11.35 at 48; 2^24 points: 74.5 ms at 128 vs 75.9 at 80;
+    // profiles/r02e_msm_tail_knobs.log, r02u_msm_chunk_sweep.log)
+    size_t target_chunk = p.total > ((size_t)1 << 27) ? 128 : (p.total > ((size_t)1 << 24) ? 96 : 48);
     if (const char* e = getenv("KZGB_MSM_CHUNK")) target_chunk = (size_t)atoi(e) > 0 ? (size_t)atoi(e) : target_chunk;
     size_t waves = (p.total + wave * target_chunk - 1) / (wave * target_chunk);
     if (waves < 1) waves = 1;

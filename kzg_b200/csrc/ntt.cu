@@ -679,10 +679,10 @@ KZGB_API int kzgb_ntt_fr(kzgb_fr* inout, uint32_t log_n, int inverse) {
     size_t bytes = (size_t)32 << log_n;
     char* d = (char*)scratch_reserve(2 * bytes);
     if (!d) return KZGB_ERR_CUDA;
-    KZG_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d, inout, bytes, lane().stream));
     int st = ntt_run((Fr*)d, (Fr*)(d + bytes), log_n, inverse != 0, lane().stream);
     if (st) return st;
-    KZG_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(inout, d, bytes, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     return KZGB_OK;
 }

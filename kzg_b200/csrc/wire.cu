@@ -278,12 +278,12 @@ KZGB_API int kzgb_fr_bytes_le(const void* in, void* out, size_t n, int to_bytes)
     char* d = (char*)staging_reserve(2 * pb + 256);
     if (!d) return KZGB_ERR_CUDA;
     int* d_bad = (int*)(d + 2 * pb);
-    KZG_CUDA(cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, lane().stream));
+    KZG_CUDA(upload_async(d, in, n * 32, lane().stream));
     KZG_CUDA(cudaMemsetAsync(d_bad, 0, 4, lane().stream));
     fr_bytes_kernel<<<div_up(n, 256), 256, 0, lane().stream>>>((const Fr*)d, (Fr*)(d + pb), n, to_bytes, d_bad);
     KZG_LAUNCHED();
     int bad = 0;
-    KZG_CUDA(cudaMemcpyAsync(out, d + pb, n * 32, cudaMemcpyDeviceToHost, lane().stream));
+    KZG_CUDA(download_async(out, d + pb, n * 32, lane().stream));
     KZG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, lane().stream));
     KZG_CUDA(cudaStreamSynchronize(lane().stream));
     if (bad) { set_error("kzgb_fr_bytes_le: non-canonical scalar (>= r)"); return KZGB_ERR_INVALID_ARG; }

@@ -245,6 +245,38 @@ def test_batched_witness_beyond_4096_points(gpu, cpu):
     srs.close()
 
 
+def test_pageable_host_inputs_take_the_pinned_relay(gpu, cpu):
+    """Host-pointer entry points accept ordinary (pageable) caller memory -- what a Rust Vec<Fr> is: large uploads go
+    through upload_async's threaded pinned relay.  Ragged sizes (not a multiple of the 2 MiB slice, more slices than ring
+    slots) must arrive byte-exact, and a commit from pageable memory must equal the one from pinned memory."""
+    import torch
+    for n in ((1 << 17) + 3, (1 << 20) + 12345, 5 * (1 << 16) * 13 + 1):
+        v = cpu.fr_stream(1000 + (n & 0xff), n)
+        h = gpu.DevicePoly(v)
+        assert (h.download() == v).all()
+        del h
+    # host NTT entry point, pageable in and out (both relays): round trip, and == the device-resident transform
+    v = cpu.fr_stream(77, 1 << 18)
+    st, fwd = gpu.ntt(v, 18)
+    h = gpu.DevicePoly(v)
+    assert st == 0 and h.ntt(18) == 0 and (h.download() == fwd).all()
+    st, back = gpu.ntt(fwd, 18, True)
+    assert st == 0 and (back == v).all()
+    n = 1 << 19
+    s = cpu.fr_stream(69, 1)[0]
+    srs = gpu.srs_generate(0, s, n)
+    sc = cpu.fr_stream(4242, n)
+    pinned = torch.from_numpy(sc.view(np.int64)).pin_memory()
+    a = srs.msm(sc)
+    b = srs.msm(pinned.numpy().view(np.uint64))
+    assert (a == b).all()
+    # twice in a row from the same lane: the ring's slots are reused across calls
+    sc2 = cpu.fr_stream(4243, n)
+    c = srs.msm(sc2)
+    d = srs.msm(torch.from_numpy(sc2.view(np.int64)).pin_memory().numpy().view(np.uint64))
+    assert (c == d).all() and not (a == c).all()
+
+
 def test_shutdown_releases_handles_and_allows_reinit():
     """kzgb_shutdown with live handles (own process): their device memory is released, a later destroy only frees the
     host side, and a re-initialised library works again (per-device kernel attributes and caches are rebuilt)."""
