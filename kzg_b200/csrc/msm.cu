@@ -191,13 +191,20 @@ KZG_DI void cp_async_wait_all_but_one() { asm volatile("cp.async.wait_group 1;" 
 #ifndef KZG_MSM_ACC_BLOCKS
 #define KZG_MSM_ACC_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(128, KZG_MSM_ACC_BLOCKS)
+#ifndef KZG_MSM_ACC_THREADS
+#define KZG_MSM_ACC_THREADS 128
+#endif
+#ifdef KZG_MSM_ACC_MAXREG   // experiments: an explicit register cap instead of the launch-bounds heuristic
+__global__ void __maxnreg__(KZG_MSM_ACC_MAXREG)
+#else
+__global__ void __launch_bounds__(KZG_MSM_ACC_THREADS, KZG_MSM_ACC_BLOCKS)
+#endif
 msm_accumulate_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                       const Affine* __restrict__ table, uint64_t total, const unsigned long long* __restrict__ zero_count,
                       uint32_t chunk, XYZZ* __restrict__ buckets, XYZZ* __restrict__ partials,
                       PartialMeta* __restrict__ meta, uint32_t nthreads) {
 #ifdef KZG_MSM_SMEM_PREFETCH
-    __shared__ uint4 pstage[2][6][128];   // [buffer][16-byte word of the point][thread]: 24 KiB, conflict-free columns
+    __shared__ uint4 pstage[2][6][KZG_MSM_ACC_THREADS];   // [buffer][16-byte word of the point][thread]: 24 KiB, conflict-free columns
 #endif
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
@@ -881,7 +888,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.total = m * (size_t)s->nwin;
     p.nb = 1u << (s->c - 1);
     // threads: a whole number of waves of (SMs * 3 blocks * 128 threads)
-    size_t wave = (size_t)c.sm_count * KZG_MSM_ACC_BLOCKS * 128;
+    size_t wave = (size_t)c.sm_count * KZG_MSM_ACC_BLOCKS * KZG_MSM_ACC_THREADS;
     // entries per accumulate thread: 48 (five waves at 2^20 x 13 windows) balances the accumulate kernel best; from ~2^21
     // points on, the boundary partials (two per thread) make the fix-up the larger term and longer chunks win
     // (2^21 points: 11.14 ms at 96 vs 11.35 at 48; 2^24 points: 74.5 ms at 128 vs 75.9 at 80;
@@ -1004,7 +1011,7 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     ctx().launches += 4;  // CUB onesweep: histogram + scan + passes (library kernels; approximate count)
     stage_end(ST_MSM_SORT, stream);
     stage_begin(ST_MSM_ACCUMULATE, stream);
-    msm_accumulate_kernel<<<div_up(p.nthreads, 128), 128, 0, stream>>>(keys1, vals1, s->table, p.total, zero, p.chunk,
+    msm_accumulate_kernel<<<div_up(p.nthreads, KZG_MSM_ACC_THREADS), KZG_MSM_ACC_THREADS, 0, stream>>>(keys1, vals1, s->table, p.total, zero, p.chunk,
                                                                       buckets, partials, meta, p.nthreads);
     KZG_LAUNCHED();
     stage_end(ST_MSM_ACCUMULATE, stream);
