@@ -22,8 +22,11 @@
  *      The Rust shim maps these to panic!, as the reference panics on
  *      out-of-range slices and failed asserts (coeff_form.rs:60, eval_form.rs:115).
  * Host-pointer entry points copy in/out on the library's own stream and return
- * when the result is in the caller's buffer (pass pinned memory for full PCIe
- * speed).  `_dev` entry points take device pointers (same layouts) and enqueue
+ * when the result is in the caller's buffer.  Pinned memory gives full PCIe
+ * speed; ordinary pageable memory (a Rust Vec<Fr>) is accepted everywhere, and
+ * transfers of 4 MiB or more are relayed through a pinned ring by a few host
+ * threads (KZGB_UPLOAD_THREADS, default 4; 0 leaves the copy to the driver).
+ * `_dev` entry points take device pointers (same layouts) and enqueue
  * on the caller-supplied CUDA stream (a cudaStream_t passed as void*; NULL =
  * the CUDA default stream) without synchronising, except where a status must
  * be read back (the witness calls).  One process drives one GPU
