@@ -418,7 +418,10 @@ def bench_single(args, env):
         scan_ms = T.timed(scan_step, 20, warmup=3)
         extra["roofline_scan"] = {"kernel": "scan_divide_linear (3 phases)", "ms": scan_ms, "algorithmic_bytes": 64 * N_POINTS,
                                   "achieved_GBps": 64 * N_POINTS / (scan_ms * 1e-3) / 1e9, "peak_GBps": hbm_peak,
-                                  "frac_hbm": 64 * N_POINTS / (scan_ms * 1e-3) / 1e9 / hbm_peak}
+                                  "frac_hbm": 64 * N_POINTS / (scan_ms * 1e-3) / 1e9 / hbm_peak,
+                                  "frac_imad": 2.6 * 136 * N_POINTS / (scan_ms * 1e-3) / imad_peak,
+                                  "binding": "int32 issue slots: a parallel Horner scan needs >= 2 Fr products (136 IMAD each) per "
+                                             "coefficient, this one 2.6 -- 41 us at the IMAD peak against 10 us of traffic (DESIGN.md 4.4)"}
         # ---- C2 witness: scan + MSM(2^20 - 1), device resident ----
         scan_step(0)
         torch.cuda.synchronize()
