@@ -157,7 +157,7 @@ void* pinned_reserve(size_t bytes) {
 
 // ---- host -> device upload with a pinned relay for pageable sources ----
 namespace {
-constexpr size_t RELAY_SLICE = size_t(2) << 20;   // bytes per pinned slice
+constexpr size_t RELAY_SLICE_MAX = size_t(2) << 20;   // bytes per pinned ring slot
 constexpr int RELAY_MAX_THREADS = 8;              // 2 slices per thread
 constexpr size_t RELAY_MIN_BYTES = size_t(4) << 20;
 
@@ -166,6 +166,16 @@ int relay_threads() {
         const char* e = getenv("KZGB_UPLOAD_THREADS");   // 0 = leave pageable copies to the driver
         int v = e ? atoi(e) : 4;
         return v < 0 ? 0 : (v > RELAY_MAX_THREADS ? RELAY_MAX_THREADS : v);
+    }();
+    return n;
+}
+
+// bytes per relayed slice (shorter slices pay more per-copy overhead than they save in pipeline fill)
+size_t relay_slice() {
+    static size_t n = [] {
+        const char* e = getenv("KZGB_UPLOAD_SLICE_KB");
+        size_t v = e ? (size_t)atol(e) << 10 : size_t(1024) << 10;   // 128 KiB .. 2 MiB measured: profiles/r02s_pageable_upload_relay.log
+        return v < 4096 ? size_t(4096) : (v > RELAY_SLICE_MAX ? RELAY_SLICE_MAX : v);
     }();
     return n;
 }
@@ -185,13 +195,14 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
     if (bytes < RELAY_MIN_BYTES || T == 0 || !host_is_pageable(src))
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
     Lane& l = lane();
-    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE);
+    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE_MAX);
     if (!ring) return cudaErrorMemoryAllocation;
     for (int i = 0; i < 2 * T; i++)
         if (!l.relay_ev[i]) {
             cudaError_t e = cudaEventCreateWithFlags(&l.relay_ev[i], cudaEventDisableTiming);
             if (e != cudaSuccess) return e;
         }
+    const size_t RELAY_SLICE = relay_slice();
     const size_t slices = (bytes + RELAY_SLICE - 1) / RELAY_SLICE;
     const int device = ctx().device;
     cudaError_t errs[RELAY_MAX_THREADS];
@@ -228,13 +239,14 @@ cudaError_t download_async(void* dst, const void* src, size_t bytes, cudaStream_
     if (bytes < RELAY_MIN_BYTES || T == 0 || !host_is_pageable(dst))
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
     Lane& l = lane();
-    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE);
+    char* ring = (char*)pinned_reserve(size_t(2 * RELAY_MAX_THREADS) * RELAY_SLICE_MAX);
     if (!ring) return cudaErrorMemoryAllocation;
     for (int i = 0; i < 2 * T; i++)
         if (!l.relay_ev[i]) {
             cudaError_t e = cudaEventCreateWithFlags(&l.relay_ev[i], cudaEventDisableTiming);
             if (e != cudaSuccess) return e;
         }
+    const size_t RELAY_SLICE = relay_slice();
     const size_t slices = (bytes + RELAY_SLICE - 1) / RELAY_SLICE;
     const int device = ctx().device;
     cudaError_t errs[RELAY_MAX_THREADS];
