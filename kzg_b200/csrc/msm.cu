@@ -637,6 +637,86 @@ __global__ void __launch_bounds__(WS_THREADS) msm_reduce_final_kernel(const XYZZ
     }
 }
 
+// The same two steps with every weight cut into a low and a high half (k = k_hi * 2^h + k_lo): the double-and-add chains
+// are half as long (they are the longest serial piece of the tail, ~7 us per point operation), the two halves run in
+// different blocks, and the factor 2^h is applied ONCE, to the sum of the high halves.  Blocks of the weighted kernel:
+// [rows low | rows high | columns low | columns high], nbr, nbr, nbc, nbc of them; partial[] in the same order.
+__global__ void __launch_bounds__(WS_THREADS) msm_weighted_sum_split_kernel(const XYZZ* __restrict__ R, uint32_t rows,
+                                                                            uint32_t rstride, const XYZZ* __restrict__ C,
+                                                                            uint32_t cols, uint32_t nbr, uint32_t nbc,
+                                                                            uint32_t h_r, uint32_t bits_r, uint32_t h_c,
+                                                                            uint32_t bits_c, XYZZ* __restrict__ partial) {
+    __shared__ XYZZ sh[WS_GROUPS];
+    const uint32_t g = threadIdx.x >> 2;
+    XYZZ base = XYZZ::inf();
+    uint32_t k = 0, h, bits, part;
+    uint32_t b = blockIdx.x;
+    if (b < 2 * nbr) {
+        part = b >= nbr;
+        uint32_t hi = (b - part * nbr) * WS_GROUPS + g;
+        if (hi < rows && hi > 0) { base = ld_xyzz(&R[(size_t)hi * rstride]); k = hi; }
+        h = h_r; bits = bits_r;
+    } else {
+        b -= 2 * nbr;
+        part = b >= nbc;
+        uint32_t lo = (b - part * nbc) * WS_GROUPS + g;
+        if (lo < cols) { base = ld_xyzz(&C[lo]); k = lo + 1; }
+        h = h_c; bits = bits_c;
+    }
+    const uint32_t kp = part ? k >> h : k & ((1u << h) - 1u);
+    XYZZ acc = xyzz_mul_small_coop(base, kp, part ? (int)(bits - h) : (int)h);
+    XYZZ tot = block_tree_sum_coop<WS_THREADS>(acc, sh);
+    if (threadIdx.x == 0) st_xyzz(&partial[blockIdx.x], tot);
+}
+
+// result = 2^log_cols * (2^h_r * sum(rows high) + sum(rows low)) + 2^h_c * sum(columns high) + sum(columns low).
+// One block of four 64-thread segments (16 groups each: 256 threads keep the full register budget), one per partial list; the four tree sums run side by side, then the row chain
+// (segment 1) and the column chain (segment 3) run in different warps.
+constexpr int RF_GROUPS = 16;               // 4-lane groups per segment
+constexpr int RF_SEG = 4 * RF_GROUPS;       // threads per segment
+constexpr int RF_THREADS = 4 * RF_SEG;
+__global__ void __launch_bounds__(RF_THREADS) msm_reduce_final_split_kernel(const XYZZ* __restrict__ partial, uint32_t nbr,
+                                                                            uint32_t nbc, uint32_t h_r, uint32_t h_c,
+                                                                            uint32_t log_cols, XYZZ* __restrict__ out) {
+    __shared__ XYZZ sh[4][RF_GROUPS];
+    const uint32_t seg = threadIdx.x / RF_SEG, g = (threadIdx.x % RF_SEG) >> 2, r = threadIdx.x & 3;
+    const uint32_t count = seg < 2 ? nbr : nbc;
+    const XYZZ* src = partial + (seg == 0 ? 0 : seg == 1 ? nbr : seg == 2 ? 2 * nbr : 2 * nbr + nbc);
+    XYZZ v = XYZZ::inf();
+    for (uint32_t i = g; i < count; i += RF_GROUPS) { XYZZ q = ld_xyzz(&src[i]); xyzz_add_coop(v, q); }
+    if (r == 0) sh[seg][g] = v;
+    __syncthreads();
+    for (uint32_t s = RF_GROUPS / 2; s > 0; s >>= 1) {
+        if (g < s) {
+            XYZZ a = sh[seg][g];
+            XYZZ b = sh[seg][g + s];
+            xyzz_add_coop(a, b);
+            v = a;
+        }
+        __syncthreads();
+        if (g < s && r == 0) sh[seg][g] = v;
+        __syncthreads();
+    }
+    if (g == 0 && (seg == 1 || seg == 3)) {   // high halves: shift, then add the low halves
+        XYZZ t = sh[seg][0];
+        const uint32_t h = seg == 1 ? h_r : h_c;
+        for (uint32_t i = 0; i < h; i++) xyzz_dbl_coop(t);
+        XYZZ lo = sh[seg - 1][0];
+        xyzz_add_coop(t, lo);
+        if (seg == 1)
+            for (uint32_t i = 0; i < log_cols; i++) xyzz_dbl_coop(t);
+        v = t;
+    }
+    __syncthreads();
+    if (g == 0 && seg == 3 && r == 0) sh[3][0] = v;
+    __syncthreads();
+    if (g == 0 && seg == 1) {
+        XYZZ c = sh[3][0];
+        xyzz_add_coop(v, c);
+        if (r == 0) st_xyzz(out, v);
+    }
+}
+
 // K6: result conversion.  mode 0: affine (blst_p1_affine), 1: Jacobian (blst_p1), 2: raw XYZZ
 __global__ void msm_finish_kernel(const XYZZ* __restrict__ in, void* __restrict__ out, int mode) {
     if (threadIdx.x) return;
@@ -927,7 +1007,7 @@ static int msm_plan(const kzgb_srs* s, size_t m, MsmPlan& p) {
     p.off_fixm0 = take((size_t)p.fix_slots * sizeof(PartialMeta));
     p.off_fixm1 = take((size_t)p.fix_slots * sizeof(PartialMeta));
     p.off_red0 = take(((size_t)p.nb + 2) * sizeof(XYZZ));  // Rb (nb/2) then Cb (nb/2)
-    p.off_red1 = take((size_t)(p.nbr + p.nbc) * sizeof(XYZZ));
+    p.off_red1 = take((size_t)2 * (p.nbr + p.nbc) * sizeof(XYZZ));   // low and high weight halves
     p.off_result = take(sizeof(XYZZ) * 2);
     p.cub_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, p.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -1095,11 +1175,22 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
             msm_reduce_final_kernel<<<1, WS_THREADS, 0, stream>>>(red1, 0, (p.nb + WS_GROUPS - 1) / WS_GROUPS, 0, result);
             KZG_LAUNCHED();
         } else {
-            msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsrc, p.rows, rstride, Csrc, p.cols, p.nbr,
-                                                                            red1);
-            KZG_LAUNCHED();
-            msm_reduce_final_kernel<<<1, WS_THREADS, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
-            KZG_LAUNCHED();
+            // weights: row hi < rows (log2 rows bits), column lo + 1 <= cols (log2 cols + 1 bits); each cut in two halves
+            const uint32_t bits_r = 31 - __builtin_clz(p.rows), bits_c = p.log_cols + 1;
+            const uint32_t h_r = (bits_r + 1) / 2, h_c = (bits_c + 1) / 2;
+            if (getenv("KZGB_MSM_UNSPLIT_WEIGHTS")) {   // the previous form, kept for A/B runs
+                msm_weighted_sum_kernel<<<p.nbr + p.nbc, WS_THREADS, 0, stream>>>(Rsrc, p.rows, rstride, Csrc, p.cols, p.nbr,
+                                                                                red1);
+                KZG_LAUNCHED();
+                msm_reduce_final_kernel<<<1, WS_THREADS, 0, stream>>>(red1, p.nbr, p.nbc, p.log_cols, result);
+                KZG_LAUNCHED();
+            } else {
+                msm_weighted_sum_split_kernel<<<2 * (p.nbr + p.nbc), WS_THREADS, 0, stream>>>(
+                    Rsrc, p.rows, rstride, Csrc, p.cols, p.nbr, p.nbc, h_r, bits_r, h_c, bits_c, red1);
+                KZG_LAUNCHED();
+                msm_reduce_final_split_kernel<<<1, RF_THREADS, 0, stream>>>(red1, p.nbr, p.nbc, h_r, h_c, p.log_cols, result);
+                KZG_LAUNCHED();
+            }
         }
     }
     stage_end(ST_MSM_BUCKET_REDUCE, stream);
