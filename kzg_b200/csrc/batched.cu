@@ -23,6 +23,7 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "batched.cuh"
+#include "batchinv.cuh"
 
 namespace kzg {
 
@@ -235,21 +236,38 @@ __global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restri
     }
 }
 
-constexpr int PD_BATCH = 32;
-// a[j] <- a[j] / z[j], inversions batched per thread
-__global__ void __launch_bounds__(128) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N) {
+#ifndef KZG_PD_BATCH
+#define KZG_PD_BATCH 16
+#endif
+#ifndef KZG_PD_THREADS
+#define KZG_PD_THREADS 128
+#endif
+#ifndef KZG_PD_MINB
+#define KZG_PD_MINB 4   // 512 blocks at 2^20: all resident, so the one-thread inversions of all blocks overlap (profiles/r02ab_block_inverse.log)
+#endif
+constexpr int PD_BATCH = KZG_PD_BATCH;
+constexpr int PD_THREADS = KZG_PD_THREADS;
+// a[j] <- a[j] / z[j]: Montgomery's trick per thread (PD_BATCH elements) and across the block (batchinv.cuh): one
+// inversion per PD_BATCH * PD_THREADS elements.  (One Kaliski inversion per 32 elements was 2/3 of this kernel's
+// instructions: 227 us at 2^20.)
+__global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N) {
+    __shared__ Fr sh[2 * PD_THREADS + 1];
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t lo = t * PD_BATCH;
-    if (lo >= N) return;
-    int cnt = (int)min((size_t)PD_BATCH, N - lo);
+    int cnt = lo < N ? (int)min((size_t)PD_BATCH, N - lo) : 0;
     Fr prefix[PD_BATCH];
     Fr acc = Fr::one();
-    for (int k = 0; k < cnt; k++) {
-        prefix[k] = acc;
-        acc = acc * b_ld(&z[lo + k]);
+#pragma unroll
+    for (int k = 0; k < PD_BATCH; k++) {
+        if (k < cnt) {
+            prefix[k] = acc;
+            acc = acc * b_ld(&z[lo + k]);
+        }
     }
-    Fr inv = acc.inv();
-    for (int k = cnt - 1; k >= 0; k--) {
+    Fr inv = block_inverse<PD_THREADS>(acc, sh);
+#pragma unroll
+    for (int k = PD_BATCH - 1; k >= 0; k--) {
+        if (k >= cnt) continue;
         Fr zi = inv * prefix[k];
         inv = inv * b_ld(&z[lo + k]);
         b_st(&a[lo + k], b_ld(&a[lo + k]) * zi);
@@ -393,7 +411,7 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
     if (st) return st;
     st = ntt_run(Zb, tmp, log_n, false, stream, 1, nullptr, (uint32_t)(m + 1));   // Z has m + 1 coefficients
     if (st) return st;
-    pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, 128), 128, 0, stream>>>(A, Zb, N);
+    pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, PD_THREADS), PD_THREADS, 0, stream>>>(A, Zb, N);
     KZG_LAUNCHED();
     st = ntt_run(A, tmp, log_n, true, stream);
     if (st) return st;

@@ -11,12 +11,19 @@
 // trick) and q_m is a block-reduced sum.
 #include "common.cuh"
 #include "field.cuh"
+#include "batchinv.cuh"
 #include "evalform.cuh"
 #include "ntt.cuh"
 
 namespace kzg {
 
-constexpr int DVO_BATCH = 16;
+#ifndef KZG_DVO_BATCH
+#define KZG_DVO_BATCH 16
+#endif
+#ifndef KZG_DVO_MINB
+#define KZG_DVO_MINB 4   // all 512 blocks of a 2^20 domain resident: the per-block inversions overlap (profiles/r02ab_block_inverse.log)
+#endif
+constexpr int DVO_BATCH = KZG_DVO_BATCH;
 constexpr int DVO_THREADS = 128;
 
 KZG_DI Fr dvo_ld(const Fr* p) {
@@ -39,15 +46,15 @@ KZG_DI Fr omega_pow(const Fr* __restrict__ tw, uint32_t e, uint32_t log_d) {
     return (e & half) ? v.neg() : v;
 }
 
-__global__ void __launch_bounds__(DVO_THREADS) div_by_omega_kernel(const Fr* __restrict__ f, uint32_t log_d, uint32_t m,
+__global__ void __launch_bounds__(DVO_THREADS, KZG_DVO_MINB) div_by_omega_kernel(const Fr* __restrict__ f, uint32_t log_d, uint32_t m,
                                                                    const Fr* __restrict__ tw, Fr* __restrict__ q,
                                                                    Fr* __restrict__ block_sums) {
-    __shared__ Fr sh[DVO_THREADS];
+    __shared__ Fr sh[2 * DVO_THREADS + 1];
     const uint32_t d = 1u << log_d;
     const uint32_t t = blockIdx.x * DVO_THREADS + threadIdx.x;
     const uint32_t lo = t * DVO_BATCH;
     Fr part = Fr::zero();
-    if (lo < d) {
+    {
         const Fr fm = dvo_ld(&f[m]);
         const Fr wm = omega_pow(tw, m, log_d);
         Fr den[DVO_BATCH], prefix[DVO_BATCH];
@@ -61,7 +68,9 @@ __global__ void __launch_bounds__(DVO_THREADS) div_by_omega_kernel(const Fr* __r
                 if (j != m) acc = acc * den[k];
             }
         }
-        Fr inv = acc.inv();
+        // one inversion per block (batchinv.cuh); threads past the end contribute 1
+        Fr inv = block_inverse<DVO_THREADS>(acc, sh);
+        __syncthreads();   // sh is reused for the block sum below
 #pragma unroll
         for (int k = DVO_BATCH - 1; k >= 0; k--) {
             uint32_t j = lo + k;
