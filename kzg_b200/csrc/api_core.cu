@@ -460,7 +460,8 @@ int kzgb_shutdown(void) {
             if (c.ntt_tw[i]) cudaFree(c.ntt_tw[i]);
             c.ntt_tw[i] = nullptr;
         }
-        c.ntt_attr_set = false;   // cudaFuncSetAttribute is per device: a re-init elsewhere must set it again
+        c.ntt_attr_set = false;
+        c.interp_attr_set = false;   // cudaFuncSetAttribute is per device: a re-init elsewhere must set it again
     }
     std::lock_guard<std::mutex> g(c.mu);
     for (Lane& l : c.lanes) {

@@ -44,9 +44,9 @@ KZG_DI void b_st(Fr* p, const Fr& v) {
 // ---- K11: interpolation ------------------------------------------------------
 // These kernels work on m <= 16384 (typically a few hundred) values: a handful of warps each, so their cost is the LENGTH OF THE DEPENDENT CHAIN
 // per thread (a dependent Fr product costs ~0.3-0.6 us), not arithmetic.  Every output is therefore computed by a
-// group of IL = 8 adjacent lanes that split the chain and combine with shuffles (field sums and products are exact,
+// group of IL = 32 adjacent lanes (a warp; 8 until the interpolation became the critical path of the batched opening) that split the chain and combine with shuffles (field sums and products are exact,
 // so the grouping does not change a single bit of the result).
-constexpr uint32_t IL = 8;
+constexpr uint32_t IL = 32;
 KZG_DI Fr fr_shfl_xor(const Fr& v, int mask) {
     Fr r;
 #pragma unroll
@@ -90,6 +90,26 @@ __global__ void __launch_bounds__(1024) interp_product_kernel(const Fr* __restri
     for (uint32_t k = threadIdx.x; k <= m; k += blockDim.x) z_out[k] = cur[k];
 }
 
+// Z(X) = prod (X - x_i) through its values: E[j] = Z(w^j) on the N-point domain, N = 2^log_n > m, followed by ONE inverse
+// NTT (deg Z = m < N, so the coefficients come back exactly).  The sequential product above is a chain of m/2 dependent
+// steps (~4 us each: 557 us at m = 256, ~10 ms at m = 4096); here every value is an independent product of m factors
+// split over IL lanes.  tw = the domain's half twiddle table (w^e, e < N/2).
+__global__ void __launch_bounds__(128) interp_zeval_kernel(const Fr* __restrict__ xs, uint32_t m, const Fr* __restrict__ tw,
+                                                           uint32_t log_n, Fr* __restrict__ E) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = gid / IL, r = gid % IL;
+    const uint32_t N = 1u << log_n, half = N >> 1;
+    const bool active = j < N;
+    Fr d = Fr::one();
+    if (active) {
+        Fr w = b_ld(&tw[j & (half - 1)]);
+        if (j & half) w = w.neg();
+        for (uint32_t i = r; i < m; i += IL) d = d * (w - xs[i]);
+    }
+    for (int o = IL / 2; o > 0; o >>= 1) d = d * fr_shfl_xor(d, o);
+    if (active && r == 0) b_st(&E[j], d);
+}
+
 // c_i = y_i / prod_{j != i} (x_i - x_j);   flag |= 2 when two x coincide (the reference panics:
 // `c.invert().unwrap()`, polynomial.rs:260).  IL lanes per i: lane r takes the factors j = r (mod IL).
 __global__ void __launch_bounds__(128) interp_weights_kernel(const Fr* __restrict__ xs, const Fr* __restrict__ ys, uint32_t m,
@@ -104,10 +124,14 @@ __global__ void __launch_bounds__(128) interp_weights_kernel(const Fr* __restric
             if (j != i) d = d * (xi - xs[j]);
     }
     for (int o = IL / 2; o > 0; o >>= 1) d = d * fr_shfl_xor(d, o);
-    if (active && r == 0) {
-        if (d.is_zero()) atomicOr(flag, 2);
-        c[i] = ys[i] * d.inv();
-    }
+    // one inversion per block (batchinv.cuh): group leaders bring their product, every other lane brings 1.  A zero
+    // product (two equal x) is replaced by 1 and flagged, so that it cannot zero the block's other results.
+    __shared__ Fr sh[2 * 128 + 1];
+    const bool lead = active && r == 0;
+    const bool zero = lead && d.is_zero();
+    if (zero) atomicOr(flag, 2);
+    Fr dinv = block_inverse<128>((lead && !zero) ? d : Fr::one(), sh);
+    if (lead) c[i] = zero ? Fr::zero() : ys[i] * dinv;
 }
 
 // T[e][i] = c_i * x_i^e.  IL lanes per i: lane r walks e = r (mod IL) with ratio x_i^IL.
@@ -121,7 +145,7 @@ __global__ void __launch_bounds__(128) interp_powers_kernel(const Fr* __restrict
 #pragma unroll
     for (uint32_t t = 1; t < IL; t <<= 1) step = step.sqr();   // x^IL (IL is a power of two)
     Fr v = c[i];
-    for (uint32_t t = 0; t < r; t++) v = v * xi;               // c * x^r
+    v = v * xi.pow_u64(r);                                     // c * x^r
     for (uint32_t e = r; e < m; e += IL) {
         b_st(&T[(size_t)e * m + i], v);
         v = v * step;
@@ -167,20 +191,21 @@ __global__ void interp_single_kernel(const Fr* __restrict__ xs, const Fr* __rest
 }
 
 // ---- K10: exact division by Z on a coset ---------------------------------------
-// s = 7^k for the smallest k >= 1 with (7^k)^N not in { x_i^N };  out = {s, s^-1}
+// s = 7^k for the smallest k >= 1 with (7^k)^N not in { x_i^N }.
+// out[0] = s, out[1] = s^-1, out[2 + i] = s^(2^i), out[2 + CS_TAB + i] = s^-(2^i) (i < CS_TAB): the scaling kernels
+// build s^lo from the table instead of a square-and-multiply ladder per thread.  7, 7^-1 and 7^N come from the host
+// (fr_util.cuh): no inversion and no squaring ladder on this single-block kernel's critical path.
+constexpr int CS_TAB = 32;
 __global__ void __launch_bounds__(256) coset_shift_kernel(const Fr* __restrict__ xs, uint32_t m, uint32_t log_n,
-                                                          Fr* __restrict__ out) {
+                                                          Fr seven, Fr seven_inv, Fr gN, Fr* __restrict__ out) {
     __shared__ int bad;
-    Fr seven = Fr::zero();
-    seven.l[0] = 7;
-    seven = seven.to_mont();
-    Fr gN = seven;
-    for (uint32_t i = 0; i < log_n; i++) gN = gN.sqr();  // 7^N
+    __shared__ Fr s_sh[2];
     Fr cand = Fr::one();
-    Fr s = Fr::one();
+    Fr s = Fr::one(), sinv = Fr::one();
     for (uint32_t k = 1; k <= m + 1; k++) {
         cand = cand * gN;  // (7^k)^N
         s = s * seven;
+        sinv = sinv * seven_inv;
         if (threadIdx.x == 0) bad = 0;
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
@@ -195,8 +220,28 @@ __global__ void __launch_bounds__(256) coset_shift_kernel(const Fr* __restrict__
     }
     if (threadIdx.x == 0) {
         out[0] = s;
-        out[1] = s.inv();
+        out[1] = sinv;
+        s_sh[0] = s;
+        s_sh[1] = sinv;
     }
+    __syncthreads();
+    if (threadIdx.x < 2 * CS_TAB) {   // thread i: i squarings of s, thread CS_TAB + i: of s^-1
+        const uint32_t i = threadIdx.x % CS_TAB;
+        Fr v = s_sh[threadIdx.x / CS_TAB];
+        for (uint32_t t = 0; t < i; t++) v = v.sqr();
+        out[2 + threadIdx.x] = v;
+    }
+}
+
+// base^e from the table tab[i] = base^(2^i)
+KZG_DI Fr pow_from_table(const Fr* __restrict__ tab, size_t e) {
+    if (e == 0) return Fr::one();
+    int i = 0;
+    while (!(e & 1)) { e >>= 1; i++; }
+    Fr r = tab[i];
+    for (e >>= 1, i++; e; e >>= 1, i++)
+        if (e & 1) r = r * tab[i];
+    return r;
 }
 
 constexpr int CS_CHUNK = 16;
@@ -209,7 +254,7 @@ __global__ void coset_scale_kernel(const Fr* __restrict__ a, size_t na, const Fr
     if (lo >= N) return;
     size_t hi = min(lo + CS_CHUNK, N);
     const Fr s = shift[0];
-    Fr pw = (lo < len) ? s.pow_u64(lo) : Fr::zero();
+    Fr pw = (lo < len) ? pow_from_table(shift + 2, lo) : Fr::zero();
     for (size_t j = lo; j < hi; j++) {
         Fr v = Fr::zero();
         if (j < len) {
@@ -229,7 +274,7 @@ __global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restri
     if (lo >= lr) return;
     size_t hi = min(lo + CS_CHUNK, lr);
     const Fr s = shift[0];
-    Fr pw = s.pow_u64(lo);
+    Fr pw = pow_from_table(shift + 2, lo);
     for (size_t j = lo; j < hi; j++) {
         b_st(&dst[j], b_ld(&dst[j]) - b_ld(&r[j]) * pw);
         pw = pw * s;
@@ -282,7 +327,7 @@ __global__ void coset_unscale_kernel(const Fr* __restrict__ q, size_t N, size_t 
     if (lo >= N) return;
     size_t hi = min(lo + CS_CHUNK, N);
     const Fr sinv = shift[1];
-    Fr pw = (lo < keep) ? sinv.pow_u64(lo) : Fr::zero();
+    Fr pw = (lo < keep) ? pow_from_table(shift + 2 + CS_TAB, lo) : Fr::zero();
     int nz = 0;
     for (size_t j = lo; j < hi; j++) {
         Fr v = b_ld(&q[j]);
@@ -314,7 +359,8 @@ static size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
 // limit (coeff_form.rs:83-111), so larger batches must be split by the caller.
 constexpr size_t KZG_MAX_BATCH_POINTS = 16384;
 
-size_t interp_workspace_bytes(size_t m) { return al((m * m + 6 * (m + 1)) * sizeof(Fr)) + 256; }
+// m x m power table + five vectors of m + 1 + two of N <= 2m (Z's values and the NTT's scratch)
+size_t interp_workspace_bytes(size_t m) { return al((m * m + 10 * (m + 2)) * sizeof(Fr)) + 256; }
 
 // d_r receives max(m,2) coefficients (m == 1: the two coefficients of X + (y - x)); d_Z receives m+1.
 int interpolate_run(const Fr* d_xs, const Fr* d_ys, size_t m, Fr* d_r, Fr* d_Z, int* d_flag, void* d_ws,
@@ -338,13 +384,33 @@ int interpolate_run(const Fr* d_xs, const Fr* d_ys, size_t m, Fr* d_r, Fr* d_Z, 
     uint32_t mm = (uint32_t)m;
     const size_t prod_smem = 2 * (m + 1) * sizeof(Fr);
     const int use_smem = prod_smem <= 96 * 1024;
-    static bool prod_attr_set = false;
-    if (use_smem && !prod_attr_set) {
-        KZG_CUDA(cudaFuncSetAttribute(interp_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        prod_attr_set = true;
+    if (use_smem) {   // per-device kernel attribute: the flag lives in the context and is reset by kzgb_shutdown
+        Context& cx = ctx();
+        std::lock_guard<std::mutex> g(cx.cache_mu);
+        if (!cx.interp_attr_set) {
+            KZG_CUDA(cudaFuncSetAttribute(interp_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            cx.interp_attr_set = true;
+        }
     }
-    interp_product_kernel<<<1, 1024, use_smem ? prod_smem : 0, stream>>>(d_xs, mm, buf0, buf1, d_Z, use_smem);
-    KZG_LAUNCHED();
+    static const bool seq_product = getenv("KZGB_INTERP_SEQ_PRODUCT") != nullptr;   // the previous form, for A/B runs
+    if (seq_product) {
+        interp_product_kernel<<<1, 1024, use_smem ? prod_smem : 0, stream>>>(d_xs, mm, buf0, buf1, d_Z, use_smem);
+        KZG_LAUNCHED();
+    } else {
+        uint32_t log_N = 1;
+        while (((size_t)1 << log_N) < m + 1) log_N++;
+        const size_t N = (size_t)1 << log_N;
+        Fr* E = T + m * m;
+        Fr* ntmp = E + N;
+        const Fr* tw = nullptr;
+        int st = ntt_get_twiddles(log_N, stream, &tw);
+        if (st) return st;
+        interp_zeval_kernel<<<div_up(N * IL, 128), 128, 0, stream>>>(d_xs, mm, tw, log_N, E);
+        KZG_LAUNCHED();
+        st = ntt_run(E, ntmp, log_N, true, stream);
+        if (st) return st;
+        KZG_CUDA(cudaMemcpyAsync(d_Z, E, (m + 1) * sizeof(Fr), cudaMemcpyDeviceToDevice, stream));
+    }
     interp_weights_kernel<<<div_up(m * IL, 128), 128, 0, stream>>>(d_xs, d_ys, mm, c, d_flag);
     KZG_LAUNCHED();
     interp_powers_kernel<<<div_up(m * IL, 128), 128, 0, stream>>>(d_xs, c, mm, T);
@@ -361,7 +427,7 @@ size_t batch_div_workspace_bytes(size_t n, size_t m) {
     if (m == 1 && L < 2) L = 2;
     uint32_t log_n = 0;
     while (((size_t)1 << log_n) < L) log_n++;
-    return 3 * al(((size_t)32) << log_n) + 512;
+    return 3 * al(((size_t)32) << log_n) + al((2 + 2 * CS_TAB) * sizeof(Fr)) + 256;
 }
 
 // psi = (p - r) div Z.  d_p: n coefficients; d_r: lr coefficients; d_Z: m+1 coefficients (monic).
@@ -392,7 +458,15 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
     Fr* Zb = (Fr*)(w + nb);
     Fr* tmp = (Fr*)(w + 2 * nb);
     Fr* shift = (Fr*)(w + 3 * nb);
-    coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, shift);
+    {
+        static const FrHost h7 = fr_host_from_u64(7), h7inv = fr_host_inv(h7);
+        const FrHost hgN = fr_host_pow(h7, (uint64_t)1 << log_n);   // 7^N (log_n < 32)
+        Fr seven, seven_inv, gN;
+        memcpy(seven.l, h7.l, 32);
+        memcpy(seven_inv.l, h7inv.l, 32);
+        memcpy(gN.l, hgN.l, 32);
+        coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, seven, seven_inv, gN, shift);
+    }
     KZG_LAUNCHED();
     unsigned gsz = div_up((N + CS_CHUNK - 1) / CS_CHUNK, 128);
     if (r_ready) {

@@ -48,6 +48,7 @@ struct Context {
     std::mutex cache_mu;
     void* ntt_tw[33] = {nullptr};
     bool ntt_attr_set = false;
+    bool interp_attr_set = false;
 };
 
 Context& ctx();
