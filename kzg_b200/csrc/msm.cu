@@ -56,17 +56,45 @@ namespace kzg {
 //   key = |d|-1 (bucket), or `nbuckets` for d == 0 (sorts to the end)
 //   val = (w*n + i) | (d < 0) << 31
 // --------------------------------------------------------------------------
+// C = 0: window width and count at run time (any c); C > 0: compile-time instance for the two production widths (limb
+// positions and shifts become constants, the loop unrolls: 68 -> see profiles/r02ad_digits.log).
+template <int C>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const Fr* __restrict__ scalars, uint32_t m, uint32_t n,
-                                                         int c, int nwin, uint32_t* __restrict__ keys,
+                                                         int c_rt, int nwin_rt, uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ vals,
                                                          unsigned long long* __restrict__ zero_count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t zeros = 0;
     if (i < m) {
-        Fr s = scalars[i].from_mont();
+        Fr s;
+        {   // two 16-byte loads (device scalar vectors are 32-byte aligned)
+            const uint4* q = reinterpret_cast<const uint4*>(&scalars[i]);
+            const uint4 a = q[0], b = q[1];
+            s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+            s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
+        }
+        s = s.from_mont();
+        const int c = C ? C : c_rt;
+        const int nwin = C ? (255 + C) / C : nwin_rt;   // ceil(256 / c): 255 scalar bits + the carry
         const uint32_t half = 1u << (c - 1);
         uint32_t carry = 0;
-        for (int w = 0; w < nwin; w++) {
+#pragma unroll
+        for (int w = 0; w < (C ? (255 + C) / C : 1); w++) {
+            if (C == 0) break;
+            const int bit = w * C;
+            const int limb = bit >> 5, off = bit & 31;
+            uint64_t v = s.l[limb < 8 ? limb : 7];
+            if (limb >= 8) v = 0;
+            if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1 < 8 ? limb + 1 : 7] << 32;
+            uint32_t d = (uint32_t)((v >> off) & ((1u << C) - 1)) + carry;
+            uint32_t neg = 0;
+            if (d > half) { d = (1u << C) - d; neg = 1; carry = 1; } else { carry = 0; }
+            uint32_t key = d ? d - 1 : half;
+            zeros += (d == 0);
+            keys[(size_t)w * m + i] = key;
+            vals[(size_t)w * m + i] = ((uint32_t)w * n + i) | (neg << 31);
+        }
+        for (int w = 0; C == 0 && w < nwin; w++) {
             int bit = w * c;
             int limb = bit >> 5, off = bit & 31;
             uint64_t v = 0;
@@ -1080,8 +1108,13 @@ int msm_run(kzgb_srs* s, const void* d_scalars, size_t m, cudaStream_t stream, c
     KZG_CUDA(cudaMemsetAsync(zero, 0, 8, stream));
     KZG_CUDA(cudaMemsetAsync(buckets, 0, (size_t)p.nb * sizeof(XYZZ), stream));
     stage_begin(ST_MSM_DIGITS, stream);
-    msm_digits_kernel<<<div_up(m, 256), 256, 0, stream>>>((const Fr*)d_scalars, (uint32_t)m, (uint32_t)s->n, s->c,
-                                                          s->nwin, keys0, vals0, zero);
+    {
+        const unsigned g = div_up(m, 256);
+        const Fr* sc = (const Fr*)d_scalars;
+        if (s->c == 20) msm_digits_kernel<20><<<g, 256, 0, stream>>>(sc, (uint32_t)m, (uint32_t)s->n, s->c, s->nwin, keys0, vals0, zero);
+        else if (s->c == 22) msm_digits_kernel<22><<<g, 256, 0, stream>>>(sc, (uint32_t)m, (uint32_t)s->n, s->c, s->nwin, keys0, vals0, zero);
+        else msm_digits_kernel<0><<<g, 256, 0, stream>>>(sc, (uint32_t)m, (uint32_t)s->n, s->c, s->nwin, keys0, vals0, zero);
+    }
     KZG_LAUNCHED();
     stage_end(ST_MSM_DIGITS, stream);
     stage_begin(ST_MSM_SORT, stream);

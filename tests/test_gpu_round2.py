@@ -277,6 +277,24 @@ def test_pageable_host_inputs_take_the_pinned_relay(gpu, cpu):
     assert (c == d).all() and not (a == c).all()
 
 
+@pytest.mark.parametrize("m", [2, 5, 9, 31, 33, 100, 129])
+def test_interpolation_with_roots_of_unity_among_the_points(gpu, cpu, m):
+    """Z(X) is built from its values on the 2^k-point domain, 2^k > m, and one inverse NTT: points that ARE roots of
+    unity of that domain (Z vanishes at some evaluation points), of the next larger one, and 0, must give the same
+    interpolant as the reference's tree recursion; m on both sides of powers of two."""
+    from kzg_b200 import scalar as S
+    N, _, omega = O.compute_omega(m + 1)
+    _, _, omega2 = O.compute_omega(2 * N)
+    special = [1, 0, omega, pow(omega, N - 1, R), omega2, pow(omega2, 3, R), R - 1]
+    xs_i = (special + [x for x in O.fr_stream(7, m) if x not in special])[:m]
+    assert len(set(xs_i)) == m
+    ys_i = O.fr_stream(8, m)
+    r = gpu.interpolate(S.fr_vec(xs_i), S.fr_vec(ys_i))
+    tree = O.SubProductTree.new_from_points(xs_i)
+    ref = O.Polynomial.lagrange_interpolation_with_tree(xs_i, ys_i, tree)
+    assert len(r) == ref.degree + 1 and S.fr_vec_int(r) == ref.coeffs[: ref.degree + 1]
+
+
 def test_shutdown_releases_handles_and_allows_reinit():
     """kzgb_shutdown with live handles (own process): their device memory is released, a later destroy only frees the
     host side, and a re-initialised library works again (per-device kernel attributes and caches are rebuilt)."""
