@@ -979,6 +979,156 @@ struct Fe {
         c = c.to_mont();
         return x * c;
     }
+    // ---- inversion by Pornin's optimised binary GCD ("Optimized Binary GCD for Modular Inversion", 2020) -------------
+    // EXPERIMENT, not used by the library (test op 12, host model): same result as inv() (the inverse is unique).  The
+    // 30 inner steps of a round run on two 62-bit approximations (low 30 bits + top 32 bits of a and b) and only the
+    // round's 2x2 update matrix touches the N-limb numbers.  Built to shorten the dependent chain where ONE thread inverts
+    // while a block or a stream waits (msm_finish_kernel, block_inverse); measured SLOWER on B200 than Kaliski's loop
+    // (msm_finish_kernel 80 vs 68 us, pointwise_div_kernel 165 vs 146 us): with 32-bit registers the 64-bit inner steps
+    // and the four signed N-limb multiply-accumulate chains per round cost as many dependent instructions as the 1.4*bits
+    // shift/subtract iterations they replace (profiles/experiments/README.md).
+    //   a = y, b = MOD, u = 1, v = 0;  invariants a = u*y, b = v*y (mod MOD);  after ROUNDS rounds a = 0, b = gcd = 1
+    //   and v = y^-1.  Parity decisions use exact low bits, so every division by 2^30 is exact; a wrong size comparison
+    //   (the approximations are not exact) only produces a negative value, which is negated together with its row.
+    // If the final b is not 1 (cannot happen for 0 < y < MOD; kept as a guard) the result comes from inv().
+    static constexpr int BG_K = 30;
+    KZG_DI static uint32_t bg_limb(const uint32_t* x, int idx) {   // x[idx] without dynamic register indexing; 0 outside
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) r = (i == idx) ? x[i] : r;
+        return r;
+    }
+    KZG_DI static int bg_bitlen(const uint32_t* x) {
+        int top = -1;
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (x[i]) { top = i; w = x[i]; }
+        if (top < 0) return 0;
+        int lz = 0;
+        while (!(w & 0x80000000u)) { w <<= 1; lz++; }
+        return 32 * top + 32 - lz;
+    }
+    KZG_DI static uint64_t bg_approx(const uint32_t* x, int n) {   // n >= 62: low 30 bits | bits [n-32, n) << 30
+        const int pos = n - 32, li = pos >> 5, off = pos & 31;
+        const uint32_t lo = bg_limb(x, li), hi = bg_limb(x, li + 1);
+        const uint32_t top = off ? ((lo >> off) | (hi << (32 - off))) : lo;
+        return (uint64_t)(x[0] & 0x3fffffffu) | ((uint64_t)top << 30);
+    }
+    // T = x*f + y*g as N+1 two's-complement limbs, returns the (sign-extended) top part; |f| + |g| <= 2^30
+    KZG_DI static int64_t bg_lincomb(const uint32_t* x, const uint32_t* y, int32_t f, int32_t g, uint32_t* T) {
+        const uint32_t af = f < 0 ? (uint32_t)(-f) : (uint32_t)f, ag = g < 0 ? (uint32_t)(-g) : (uint32_t)g;
+        int64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const int64_t pf = (int64_t)((uint64_t)x[i] * af), pg = (int64_t)((uint64_t)y[i] * ag);   // < 2^62 each
+            acc += (f < 0 ? -pf : pf) + (g < 0 ? -pg : pg);
+            T[i] = (uint32_t)acc;
+            acc >>= 32;
+        }
+        T[N] = (uint32_t)acc;
+        return acc;
+    }
+    KZG_DI static void bg_shift30(const uint32_t* T, uint32_t* out) {   // out = low N limbs of (T >> 30)
+#pragma unroll
+        for (int i = 0; i < N; i++) out[i] = (T[i] >> 30) | (T[i + 1] << 2);
+    }
+    KZG_DI static void bg_negate(uint32_t* x) {
+        uint32_t c = 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t t = ~x[i] + c;
+            c = (c && t == 0) ? 1u : 0u;
+            x[i] = t;
+        }
+    }
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+    static long& bingcd_fallbacks() { static long n = 0; return n; }
+#endif
+    __device__ __noinline__ Fe inv_bingcd() const {
+        if (is_zero()) return zero();
+        uint32_t a[N], b[N], u[N], v[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { a[i] = l[i]; b[i] = P::mod(i); u[i] = 0; v[i] = 0; }
+        u[0] = 1;
+        const uint32_t minv = P::inv32();   // -MOD^-1 mod 2^32
+        constexpr int BG_ROUNDS = (2 * bits() - 1 + BG_K - 1) / BG_K + 1;   // Pornin: 2*len - 1 inner steps suffice; one spare round
+#pragma unroll 1
+        for (int round = 0; round < BG_ROUNDS; round++) {
+            int n = bg_bitlen(a), nb = bg_bitlen(b);
+            n = n > nb ? n : nb;
+            n = n > 62 ? n : 62;
+            uint64_t xa = bg_approx(a, n), xb = bg_approx(b, n);
+            int32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+#pragma unroll 1
+            for (int j = 0; j < BG_K; j++) {
+                if (xa & 1) {
+                    if (xa < xb) {
+                        const uint64_t tx = xa; xa = xb; xb = tx;
+                        int32_t t = f0; f0 = f1; f1 = t;
+                        t = g0; g0 = g1; g1 = t;
+                    }
+                    xa -= xb; f0 -= f1; g0 -= g1;
+                }
+                xa >>= 1; f1 <<= 1; g1 <<= 1;
+            }
+            // (a, b) <- ((a f0 + b g0) / 2^30, (a f1 + b g1) / 2^30), made non-negative together with their rows
+            uint32_t T[N + 1], na[N], nbv[N];
+            if (bg_lincomb(a, b, f0, g0, T) < 0) { bg_shift30(T, na); bg_negate(na); f0 = -f0; g0 = -g0; }
+            else bg_shift30(T, na);
+            if (bg_lincomb(a, b, f1, g1, T) < 0) { bg_shift30(T, nbv); bg_negate(nbv); f1 = -f1; g1 = -g1; }
+            else bg_shift30(T, nbv);
+            // (u, v) <- the same combinations divided by 2^30 modulo MOD: add t*MOD with t = -T/MOD mod 2^30 first
+            uint32_t nu[N], nv[N];
+#pragma unroll
+            for (int row = 0; row < 2; row++) {
+                int64_t hi = bg_lincomb(u, v, row ? f1 : f0, row ? g1 : g0, T);
+                const uint32_t t = (T[0] * minv) & 0x3fffffffu;
+                uint64_t c = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    c += (uint64_t)t * P::mod(i) + T[i];
+                    T[i] = (uint32_t)c;
+                    c >>= 32;
+                }
+                hi += (int64_t)c;
+                T[N] = (uint32_t)hi;
+                uint32_t* out = row ? nv : nu;
+                bg_shift30(T, out);                  // value in (-MOD, 2 MOD), two's complement if negative
+                Fe w;
+#pragma unroll
+                for (int i = 0; i < N; i++) w.l[i] = out[i];
+                if (hi < 0) {                        // += MOD
+                    w.l[0] = add_cc(w.l[0], P::mod(0));
+#pragma unroll
+                    for (int i = 1; i < N - 1; i++) w.l[i] = addc_cc(w.l[i], P::mod(i));
+                    w.l[N - 1] = addc(w.l[N - 1], P::mod(N - 1));
+                } else {
+                    w.final_sub();
+                }
+#pragma unroll
+                for (int i = 0; i < N; i++) out[i] = w.l[i];
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++) { a[i] = na[i]; b[i] = nbv[i]; u[i] = nu[i]; v[i] = nv[i]; }
+        }
+        uint32_t rest = b[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; i++) rest |= b[i];
+#pragma unroll
+        for (int i = 0; i < N; i++) rest |= a[i];
+        if (rest) {                                  // guard: not reached for 0 < y < MOD (the host model counts it)
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+            bingcd_fallbacks()++;
+#endif
+            return inv();
+        }
+        // v = (x R)^-1 as a plain integer; (x R)^-1 * R^3 / R = x^-1 R
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = v[i];
+        return r * (r2() * r2());
+    }
     __host__ __device__ static constexpr int bits() {
         int b = 32 * N;
         uint32_t top = P::mod(N - 1);

@@ -7,7 +7,7 @@
 namespace kzg {
 
 // op: 0 mul, 1 add, 2 sub, 3 inv(a), 4 to_mont(a), 5 from_mont(a), 6 sqr(a), 7 inv_fermat(a), 8 mul via the FP64 pipe,
-//     9 Karatsuba mul, 10/11 lazy-reduction a*b - c*d
+//     9 Karatsuba mul, 10/11 lazy-reduction a*b - c*d, 12 inv by Pornin's binary GCD
 template <class F>
 __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b, F* __restrict__ o, size_t n, int op) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -25,6 +25,7 @@ __global__ void fe_binop_kernel(const F* __restrict__ a, const F* __restrict__ b
         case 9: r = F::mul_kara(x, y); break;                      // Karatsuba product + ripple-free reduction
         case 10: r = F::mul_sub_mul(x, y, x + y, y); break;        // lazy reduction: x*y - (x+y)*y = -y^2
         case 11: r = F::mul_sub_mul(x, y, y, x.sqr()); break;      // x*y - y*x^2
+        case 12: r = x.inv_bingcd(); break;                        // experiment: binary GCD on word-size approximations
         default: r = x.sqr(); break;
     }
     o[i] = r;

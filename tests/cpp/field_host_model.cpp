@@ -10,6 +10,10 @@
 
 #include "../../kzg_b200/csrc/field.cuh"
 
+// the two funnel shifts Fe::inv() (Kaliski) uses, for the host build
+unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
+unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+
 using namespace kzg;
 typedef unsigned __int128 u128;
 
@@ -165,6 +169,33 @@ static int run(const char* name, int iters) {
             memcpy(pm.l, m, 8 * W);
             if (!z.is_zero_modp() || !pm.is_zero_modp() || (!a.is_zero() && la.is_zero_modp())) { printf("%s: is_zero_modp at %d\n", name, it); bad++; }
         }
+    }
+    // ---- inversion: Pornin's binary GCD (inv_bingcd, an experiment) against Kaliski's almost-inverse (inv) and against x * x^-1 = 1
+    {
+        F one = F::one();
+        uint64_t m[W];
+        Model<P>::mod64(m);
+        const int n_inv = iters / 20 + 200;
+        for (int it = 0; it < n_inv && bad < 5; it++) {
+            F a;
+            random_fe<P>(a, it < 60 ? it % 6 : 0);
+            if (it >= 60 && it < 60 + 32 * P::N) {          // single bits, and MOD minus single bits
+                memset(a.l, 0, sizeof(a.l));
+                a.l[(it - 60) / 32] = 1u << ((it - 60) % 32);
+                uint64_t v[W];
+                memcpy(v, a.l, 8 * W);
+                if (Model<P>::geq(v, m)) continue;
+                if (it & 1) { uint64_t z[W] = {0}, r[W]; Model<P>::submod(r, z, v); memcpy(a.l, r, 8 * W); }
+            }
+            F g = a.inv_bingcd(), k = a.inv();
+            uint64_t prod[W], ma[W], mg[W];
+            memcpy(ma, a.l, 8 * W); memcpy(mg, g.l, 8 * W);
+            Model<P>::mul(prod, ma, mg);
+            const bool ok = a.is_zero() ? g.is_zero() : (memcmp(prod, one.l, 8 * W) == 0);
+            if (!ok || memcmp(g.l, k.l, 8 * W)) { printf("%s: inv (binary GCD) mismatch at %d\n", name, it); bad++; }
+        }
+        printf("%s: %d inversions checked, %ld fell back to Kaliski\n", name, n_inv, F::bingcd_fallbacks());
+        if (F::bingcd_fallbacks()) bad++;
     }
     printf("%s: %d iterations, %d mismatches\n", name, iters, bad);
     return bad;

@@ -295,6 +295,31 @@ def test_interpolation_with_roots_of_unity_among_the_points(gpu, cpu, m):
     assert len(r) == ref.degree + 1 and S.fr_vec_int(r) == ref.coeffs[: ref.degree + 1]
 
 
+def test_inversion_three_ways(gpu, cpu):
+    """inv() (Kaliski's almost-inverse), the Fermat chain (op 7) and the binary GCD on word-size approximations (op 12: an
+    experiment kept in field.cuh, measured slower) must agree with each other and with the integers, on random values and
+    on edge values: 0, 1, MOD - 1, single bits, values just below the modulus, tiny values."""
+    from kzg_b200 import scalar as S
+    n = 1024
+    edge_r = [0, 1, 2, 3, R - 1, R - 2, (R - 1) // 2, (R + 1) // 2] + [1 << k for k in range(0, 255, 7)] + [R - (1 << k) for k in range(0, 254, 9)]
+    a = np.vstack([S.fr_vec(edge_r), cpu.fr_stream(31, n)])
+    got = gpu.test_fr_op(a, None, 3)
+    assert (got == gpu.test_fr_op(a, None, 12)).all() and (got == gpu.test_fr_op(a, None, 7)).all()
+    vals = S.fr_vec_int(a)
+    assert S.fr_vec_int(got) == [pow(x, -1, R) if x else 0 for x in vals]
+    P = O.P_MOD
+    edge_p = [0, 1, 2, P - 1, P - 2, (P - 1) // 2] + [1 << k for k in range(0, 381, 11)] + [P - (1 << k) for k in range(0, 380, 13)]
+    rng = np.random.default_rng(77)
+    fa = rng.integers(0, 2 ** 63, size=(n, 6), dtype=np.uint64)
+    fa[:, 5] &= np.uint64(0x0fffffffffffffff)
+    fa = np.vstack([np.array([O.fq_to_mont_limbs(x) for x in edge_p], dtype=np.uint64), fa])
+    g = gpu.test_fp_op(fa, None, 3)
+    assert (g == gpu.test_fp_op(fa, None, 12)).all() and (g == gpu.test_fp_op(fa, None, 7)).all()
+    for k in list(range(len(edge_p))) + [len(edge_p) + 5, len(edge_p) + 77]:
+        x = O.fq_from_mont_limbs(fa[k])
+        assert O.fq_from_mont_limbs(g[k]) == (pow(x, -1, P) if x else 0)
+
+
 def test_shutdown_releases_handles_and_allows_reinit():
     """kzgb_shutdown with live handles (own process): their device memory is released, a later destroy only frees the
     host side, and a re-initialised library works again (per-device kernel attributes and caches are rebuilt)."""
