@@ -281,6 +281,26 @@ __global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restri
     }
 }
 
+// Z on the coset s*H_N through N/M transforms of size M = 2^log_m > m instead of one of size N: with j = a + (N/M) b,
+// Z(s w_N^j) = sum_k [z_k (s w_N^a)^k] w_M^(b k), i.e. row a of dst is the M-point transform of Z's coefficients scaled
+// by powers of s w_N^a (m + 1 of them; the rest of the row is zero: the caller clears dst).  log2 M instead of log2 N
+// butterfly stages per element.  tw = half twiddle table of the N-point domain.
+__global__ void __launch_bounds__(128) coset_fill_z_kernel(const Fr* __restrict__ Z, uint32_t m, const Fr* __restrict__ tw,
+                                                           uint32_t log_cn, uint32_t log_m, const Fr* __restrict__ shift,
+                                                           Fr* __restrict__ dst) {
+    const uint32_t chunks = (m + 1 + CS_CHUNK - 1) / CS_CHUNK;
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t a = idx / chunks;
+    if (a >> log_cn) return;
+    const uint32_t k0 = (uint32_t)(idx % chunks) * CS_CHUNK, k1 = min(k0 + CS_CHUNK, m + 1);
+    const Fr base = shift[0] * b_ld(&tw[a]);   // a < N/M <= N/2
+    Fr pw = base.pow_u64(k0);
+    for (uint32_t k = k0; k < k1; k++) {
+        b_st(&dst[(a << log_m) + k], b_ld(&Z[k]) * pw);
+        pw = pw * base;
+    }
+}
+
 #ifndef KZG_PD_BATCH
 #define KZG_PD_BATCH 16
 #endif
@@ -295,7 +315,11 @@ constexpr int PD_THREADS = KZG_PD_THREADS;
 // a[j] <- a[j] / z[j]: Montgomery's trick per thread (PD_BATCH elements) and across the block (batchinv.cuh): one
 // inversion per PD_BATCH * PD_THREADS elements.  (One Kaliski inversion per 32 elements was 2/3 of this kernel's
 // instructions: 227 us at 2^20.)
-__global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N) {
+// z is either in natural order (log_cn = 0) or in the sub-coset layout of coset_fill_z_kernel: the value for index j sits
+// at (j mod 2^log_cn) * 2^log_m + (j >> log_cn).
+__global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(Fr* __restrict__ a, const Fr* __restrict__ z, size_t N,
+                                                                                uint32_t log_cn, uint32_t log_m) {
+    auto zi_of = [&](size_t j) { return ((j & (((size_t)1 << log_cn) - 1)) << log_m) + (j >> log_cn); };
     __shared__ Fr sh[2 * PD_THREADS + 1];
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t lo = t * PD_BATCH;
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(
     for (int k = 0; k < PD_BATCH; k++) {
         if (k < cnt) {
             prefix[k] = acc;
-            acc = acc * b_ld(&z[lo + k]);
+            acc = acc * b_ld(&z[zi_of(lo + k)]);
         }
     }
     Fr inv = block_inverse<PD_THREADS>(acc, sh);
@@ -314,7 +338,7 @@ __global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(
     for (int k = PD_BATCH - 1; k >= 0; k--) {
         if (k >= cnt) continue;
         Fr zi = inv * prefix[k];
-        inv = inv * b_ld(&z[lo + k]);
+        inv = inv * b_ld(&z[zi_of(lo + k)]);
         b_st(&a[lo + k], b_ld(&a[lo + k]) * zi);
     }
 }
@@ -479,13 +503,30 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
         coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, A);
         KZG_LAUNCHED();
     }
-    coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, Zb);
-    KZG_LAUNCHED();
-    int st = ntt_run(A, tmp, log_n, false, stream);
+    uint32_t log_m = 1;
+    while (((size_t)1 << log_m) < m + 1) log_m++;
+    const bool small_z = log_m + 1 <= log_n && (log_n - log_m) <= 15 && !getenv("KZGB_BATCH_FULL_Z_NTT");
+    const uint32_t log_cn = small_z ? log_n - log_m : 0;
+    int st;
+    if (small_z) {   // N/M transforms of size M (see coset_fill_z_kernel)
+        const Fr* twN = nullptr;
+        st = ntt_get_twiddles(log_n, stream, &twN);
+        if (st) return st;
+        KZG_CUDA(cudaMemsetAsync(Zb, 0, N * sizeof(Fr), stream));
+        const size_t work = ((size_t)1 << log_cn) * ((m + 1 + CS_CHUNK - 1) / CS_CHUNK);
+        coset_fill_z_kernel<<<div_up(work, 128), 128, 0, stream>>>(d_Z, (uint32_t)m, twN, log_cn, log_m, shift, Zb);
+        KZG_LAUNCHED();
+    } else {
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, Zb);
+        KZG_LAUNCHED();
+    }
+    st = ntt_run(A, tmp, log_n, false, stream);
     if (st) return st;
-    st = ntt_run(Zb, tmp, log_n, false, stream, 1, nullptr, (uint32_t)(m + 1));   // Z has m + 1 coefficients
+    if (small_z) st = ntt_run(Zb, tmp, log_m, false, stream, 1u << log_cn);
+    else st = ntt_run(Zb, tmp, log_n, false, stream, 1, nullptr, (uint32_t)(m + 1));   // Z has m + 1 coefficients
     if (st) return st;
-    pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, PD_THREADS), PD_THREADS, 0, stream>>>(A, Zb, N);
+    pointwise_div_kernel<<<div_up((N + PD_BATCH - 1) / PD_BATCH, PD_THREADS), PD_THREADS, 0, stream>>>(A, Zb, N, log_cn,
+                                                                                                   small_z ? log_m : 0);
     KZG_LAUNCHED();
     st = ntt_run(A, tmp, log_n, true, stream);
     if (st) return st;
