@@ -27,3 +27,16 @@ xy = torch.from_numpy(np.vstack([cpu.fr_stream(7, 1)[0], np.zeros(4, dtype=np.ui
 work = torch.empty((n, 4), dtype=torch.int64, device=dev)
 _ffi.witness_coeff_dev(srs, sc.data_ptr(), n, xy.data_ptr(), work.data_ptr(), out.data_ptr(), 0)
 torch.cuda.synchronize()
+# one batched opening (256 points on the polynomial)
+m = 256
+xs = torch.empty((m, 4), dtype=torch.int64, device=dev); _ffi.fr_stream_dev(xs.data_ptr(), 7, m)
+ys = torch.empty((m, 4), dtype=torch.int64, device=dev)
+import ctypes as C
+lib = _ffi.lib()
+xy2 = torch.zeros((2, 4), dtype=torch.int64, device=dev)
+for i in range(m):
+    xy2[0] = xs[i]
+    lib.kzgb_divide_linear_dev(C.c_void_p(sc.data_ptr()), C.c_size_t(n), C.c_void_p(xy2.data_ptr()), C.c_int(0), C.c_void_p(work.data_ptr()), C.c_void_p(ys[i].data_ptr()), C.c_void_p(0))
+r = torch.zeros((m + 2, 4), dtype=torch.int64, device=dev)
+print("batched status", _ffi.witness_batched_dev(srs, sc.data_ptr(), n, xs.data_ptr(), ys.data_ptr(), m, r.data_ptr(), out.data_ptr(), 0))
+torch.cuda.synchronize()
