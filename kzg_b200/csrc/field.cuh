@@ -218,10 +218,12 @@ struct Fe {
 #pragma unroll
         for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
         uint32_t borrow = subc(0, 0);  // all ones if a < b
-        r.l[0] = add_cc(r.l[0], P::mod(0) & borrow);
+        if (borrow) {   // predicated adds of immediates: no AND per limb
+            r.l[0] = add_cc(r.l[0], P::mod(0));
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i) & borrow);
-        r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1) & borrow);
+            for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(r.l[i], P::mod(i));
+            r.l[N - 1] = addc(r.l[N - 1], P::mod(N - 1));
+        }
         return r;
     }
     KZG_DI Fe neg() const { return zero() - *this; }

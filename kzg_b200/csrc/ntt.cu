@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
                 Fr w = twiddle(tw, e0, p.log_n, p.inverse, neg);
                 t = t * w;
             }
-            Fr a = u + t, c = u - t;
-            sm_st(sm, i0, E, neg ? c : a);
-            sm_st(sm, i1, E, neg ? a : c);
+            // a twiddle in the upper half of the circle is minus a table entry: the two results trade PLACES (one select
+            // on the slot index instead of eight on the limbs of each value)
+            sm_st(sm, neg ? i1 : i0, E, u + t);
+            sm_st(sm, neg ? i0 : i1, E, u - t);
         }
         __syncthreads();
         s = 1;
@@ -199,38 +200,43 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
             Fr x0 = sm_ld(sm, i0, E), x1 = sm_ld(sm, i1, E), x2 = sm_ld(sm, i2, E), x3 = sm_ld(sm, i3, E);
             const uint32_t kap = LAST ? (p.fold ? (uint32_t)(k10 + tl) + ((uint32_t)k2 << p.log_r1) : 0u) : kap_tile;
             const uint32_t kbase = kap << p.log_nj;     // kappa * N_j  (< N)
+            // A twiddle in the upper half of the circle is MINUS a table entry (twiddle() reports it as `neg`): sum and
+            // difference of that butterfly trade places.  The swap is carried on INDICES -- which exponent the next
+            // stage's pair uses, which slot a result is stored to -- not on the eight limbs of every value (16 selects
+            // per butterfly, 9 % of the non-multiply instructions of a pass).
             // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m + kappa * N_j/2m)
+            bool negA = false;
             {
-                bool neg = false;
                 const uint32_t e1 = (j << (p.log_n - s - 1)) + (kbase >> (s + 1));
                 if (e1 != 0) {
-                    Fr w = twiddle(tw, e1, p.log_n, p.inverse, neg);
+                    Fr w = twiddle(tw, e1, p.log_n, p.inverse, negA);
                     x1 = x1 * w;
                     x3 = x3 * w;
                 }
-                Fr a = x0 + x1, c = x0 - x1, d = x2 + x3, e = x2 - x3;
-                x0 = neg ? c : a; x1 = neg ? a : c; x2 = neg ? e : d; x3 = neg ? d : e;
             }
-            // stage s+1: (x0,x2) with w^(j * N/4m + kappa * N_j/4m), (x1,x3) with w^((j+m) * N/4m + kappa * N_j/4m)
+            const Fr y0 = x0 + x1, y1 = x0 - x1, y2 = x2 + x3, y3 = x2 - x3;   // logical (Y0,Y1,Y2,Y3) = negA ? (y1,y0,y3,y2) : (y0,y1,y2,y3)
+            // stage s+1: logical pair (Y0,Y2) with w^(j * N/4m + kappa * N_j/4m) -> slots (i0,i2); logical pair (Y1,Y3) with
+            // w^((j+m) * N/4m + kappa * N_j/4m) -> slots (i1,i3).  Registers (y0,y2) are the first pair unless negA.
+            const uint32_t e2 = (j << (p.log_n - s - 2)) + (kbase >> (s + 2));
+            const uint32_t e3 = ((j + m) << (p.log_n - s - 2)) + (kbase >> (s + 2));
             {
+                const uint32_t ep = negA ? e3 : e2;
+                const uint32_t lo = negA ? i1 : i0, hi = negA ? i3 : i2;
                 bool neg = false;
-                const uint32_t e2 = (j << (p.log_n - s - 2)) + (kbase >> (s + 2));
-                if (e2 != 0) {
-                    Fr w = twiddle(tw, e2, p.log_n, p.inverse, neg);
-                    x2 = x2 * w;
-                }
-                Fr a = x0 + x2, c = x0 - x2;
-                x0 = neg ? c : a; x2 = neg ? a : c;
-                bool neg2 = false;
-                Fr w2 = twiddle(tw, ((j + m) << (p.log_n - s - 2)) + (kbase >> (s + 2)), p.log_n, p.inverse, neg2);
-                x3 = x3 * w2;
-                Fr d = x1 + x3, e = x1 - x3;
-                x1 = neg2 ? e : d; x3 = neg2 ? d : e;
+                Fr t = y2;
+                if (ep != 0) t = t * twiddle(tw, ep, p.log_n, p.inverse, neg);
+                sm_st(sm, neg ? hi : lo, E, y0 + t);
+                sm_st(sm, neg ? lo : hi, E, y0 - t);
             }
-            sm_st(sm, i0, E, x0);
-            sm_st(sm, i1, E, x1);
-            sm_st(sm, i2, E, x2);
-            sm_st(sm, i3, E, x3);
+            {
+                const uint32_t ep = negA ? e2 : e3;
+                const uint32_t lo = negA ? i0 : i1, hi = negA ? i2 : i3;
+                bool neg = false;
+                Fr t = y3;
+                if (ep != 0) t = t * twiddle(tw, ep, p.log_n, p.inverse, neg);
+                sm_st(sm, neg ? hi : lo, E, y1 + t);
+                sm_st(sm, neg ? lo : hi, E, y1 - t);
+            }
         }
         __syncthreads();
     }
