@@ -116,7 +116,13 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
     // the conflicts: bit-reversed rows while staging, rows 4*gg in the first radix-4 step -- all multiples of 32 or 4
     // slots, i.e. the same bank group (ncu, round 1: 3.5 M conflicts per pass).  Folding the upper slot bits onto the low
     // three (slot ^= slot>>3 ^ slot>>6 ^ slot>>9, mod 8) makes every power-of-two stride conflict-free.
+    // (an experiment that changed nothing measurable; it is compiled out by default -- as a run-time flag it cost three
+    // instructions in every slot computation of the hot loop: build with -DKZG_NTT_GENERIC_SWZ to get KZGB_NTT_SWZ=1 back)
+#ifdef KZG_NTT_GENERIC_SWZ
     const bool gswz = !LAST && p.swz;
+#else
+    constexpr bool gswz = false;
+#endif
     auto SW = [&](uint32_t row, uint32_t col) {
         uint32_t slot = (row << p.log_t) + (col ^ ((row >> sw_shift) & sw_mask));
         if (gswz) slot ^= ((slot >> 3) ^ (slot >> 6) ^ (slot >> 9)) & 7u;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
             const uint32_t kap = LAST ? (p.fold ? (uint32_t)(k10 + tl) + ((uint32_t)k2 << p.log_r1) : 0u) : kap_tile;
             const uint32_t e0 = (kap << p.log_nj) >> 1;
             bool neg = false;
-            if (e0 != 0) {
+            if (LAST || kap_tile != 0) {   // block-uniform test (a lane-wise `e0 != 0` diverges and saves nothing)
                 Fr w = twiddle(tw, e0, p.log_n, p.inverse, neg);
                 t = t * w;
             }
@@ -205,14 +211,16 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
             // stage's pair uses, which slot a result is stored to -- not on the eight limbs of every value (16 selects
             // per butterfly, 9 % of the non-multiply instructions of a pass).
             // stage s: (x0,x1) and (x2,x3), twiddle w^(j * N/2m + kappa * N_j/2m)
+            // Unit twiddles are skipped only where the test is uniform over the block: the first stage (m = 1, j = 0) of a
+            // tile with kappa = 0 (every tile of the first pass).  Elsewhere a lane whose exponent happens to be 0
+            // multiplies by table[0] = 1: exact, and cheaper than a divergent branch around the product.
+            const bool unit_first = !LAST && kap_tile == 0 && s == 0;
             bool negA = false;
-            {
+            if (!unit_first) {
                 const uint32_t e1 = (j << (p.log_n - s - 1)) + (kbase >> (s + 1));
-                if (e1 != 0) {
-                    Fr w = twiddle(tw, e1, p.log_n, p.inverse, negA);
-                    x1 = x1 * w;
-                    x3 = x3 * w;
-                }
+                Fr w = twiddle(tw, e1, p.log_n, p.inverse, negA);
+                x1 = x1 * w;
+                x3 = x3 * w;
             }
             const Fr y0 = x0 + x1, y1 = x0 - x1, y2 = x2 + x3, y3 = x2 - x3;   // logical (Y0,Y1,Y2,Y3) = negA ? (y1,y0,y3,y2) : (y0,y1,y2,y3)
             // stage s+1: logical pair (Y0,Y2) with w^(j * N/4m + kappa * N_j/4m) -> slots (i0,i2); logical pair (Y1,Y3) with
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
                 const uint32_t lo = negA ? i1 : i0, hi = negA ? i3 : i2;
                 bool neg = false;
                 Fr t = y2;
-                if (ep != 0) t = t * twiddle(tw, ep, p.log_n, p.inverse, neg);
+                if (!unit_first) t = t * twiddle(tw, ep, p.log_n, p.inverse, neg);   // unit_first: negA = false, ep = e2 = 0
                 sm_st(sm, neg ? hi : lo, E, y0 + t);
                 sm_st(sm, neg ? lo : hi, E, y0 - t);
             }
@@ -232,8 +240,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const Fr* in, 
                 const uint32_t ep = negA ? e2 : e3;
                 const uint32_t lo = negA ? i0 : i1, hi = negA ? i2 : i3;
                 bool neg = false;
-                Fr t = y3;
-                if (ep != 0) t = t * twiddle(tw, ep, p.log_n, p.inverse, neg);
+                Fr t = y3 * twiddle(tw, ep, p.log_n, p.inverse, neg);
                 sm_st(sm, neg ? hi : lo, E, y1 + t);
                 sm_st(sm, neg ? lo : hi, E, y1 - t);
             }
