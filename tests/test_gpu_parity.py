@@ -247,7 +247,7 @@ def test_ntt_full_size_properties(gpu, cpu, log_n):
 
 
 # ------------------------------------------------------------------ K9 linear quotient
-@pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 4095, 4096, 4097, 65541])
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 2047, 2048, 2049, 4095, 4096, 4097, 6145, 65541])
 def test_divide_linear_matches_long_division(gpu, cpu, n):
     p = cpu.fr_stream(42, n)
     x = cpu.fr_stream(7, 1)[0]
