@@ -148,8 +148,13 @@ KZG_DI void madd_hot(XYZZ& acc, const Fq& x2, const Fq& y2) {
         acc.x = x2; acc.y = y2; acc.zz = Fq::one(); acc.zzz = Fq::one();
         return;
     }
+#if defined(KZG_MSM_INLINE_PRODUCTS) && KZG_MSM_INLINE_PRODUCTS >= 4   // experiment: some products inline (no argument marshalling, more code)
+    Fq P = Fq::sub_lazy(Fq::mul_inline<false>(x2, acc.zz), acc.x);
+    Fq R = Fq::sub_lazy(Fq::mul_inline<false>(y2, acc.zzz), acc.y);
+#else
     Fq P = Fq::sub_lazy(Fq::mul_lazy_outlined(x2, acc.zz), acc.x);
     Fq R = Fq::sub_lazy(Fq::mul_lazy_outlined(y2, acc.zzz), acc.y);
+#endif
     if (P.is_zero_modp()) {
         xyzz_madd_rare(acc, x2, y2, R.is_zero_modp());
         return;
@@ -157,8 +162,13 @@ KZG_DI void madd_hot(XYZZ& acc, const Fq& x2, const Fq& y2) {
     Fq PP = Fq::sqr_lazy_outlined(P);
     Fq PPP = Fq::mul_lazy_outlined(P, PP);
     Fq Q = Fq::mul_lazy_outlined(acc.x, PP);
+#if defined(KZG_MSM_INLINE_PRODUCTS) && KZG_MSM_INLINE_PRODUCTS >= 2
+    acc.zz = Fq::mul_inline<false>(acc.zz, PP);
+    acc.zzz = Fq::mul_inline<false>(acc.zzz, PPP);
+#else
     acc.zz = Fq::mul_lazy_outlined(acc.zz, PP);
     acc.zzz = Fq::mul_lazy_outlined(acc.zzz, PPP);
+#endif
     Fq X3 = Fq::sub_lazy(Fq::sub_lazy(Fq::sqr_lazy_outlined(R), PPP), Q.dbl_lazy());
     acc.y = Fq::mul_add_mul_lazy_outlined(R, Fq::sub_lazy(Q, X3), acc.y.neg_lazy(), PPP);
     acc.x = X3;
