@@ -453,7 +453,10 @@ constexpr uint32_t FIX_F_MAX = 30;
 constexpr uint32_t FIX_PEEK = 4;
 
 template <bool COOP>
-__global__ void __launch_bounds__(128) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
+#ifndef KZG_FIX_MINB
+#define KZG_FIX_MINB 1
+#endif
+__global__ void __launch_bounds__(128, KZG_FIX_MINB) msm_fixup_level_kernel(const XYZZ* __restrict__ pin,
                                                               const PartialMeta* __restrict__ min_, uint32_t nslots_in,
                                                               XYZZ* __restrict__ buckets, XYZZ* __restrict__ pout,
                                                               PartialMeta* __restrict__ mout, uint32_t nthreads,
