@@ -275,6 +275,11 @@ def test_pageable_host_inputs_take_the_pinned_relay(gpu, cpu):
     c = srs.msm(sc2)
     d = srs.msm(torch.from_numpy(sc2.view(np.int64)).pin_memory().numpy().view(np.uint64))
     assert (c == d).all() and not (a == c).all()
+    # the pipelined batch entry point uploads on its own copy stream: pageable items above the relay threshold, mixed
+    # with a short one, must give the single-call results
+    items = [sc, sc2[: (1 << 17) + 5], sc[:100], sc2]
+    singles = np.stack([srs.msm(x) for x in items])
+    assert (srs.msm_batch(items) == singles).all()
 
 
 @pytest.mark.parametrize("m", [2, 5, 9, 31, 33, 100, 129])
