@@ -195,32 +195,49 @@ __global__ void interp_single_kernel(const Fr* __restrict__ xs, const Fr* __rest
 // out[0] = s, out[1] = s^-1, out[2 + i] = s^(2^i), out[2 + CS_TAB + i] = s^-(2^i) (i < CS_TAB): the scaling kernels
 // build s^lo from the table instead of a square-and-multiply ladder per thread.  7, 7^-1 and 7^N come from the host
 // (fr_util.cuh): no inversion and no squaring ladder on this single-block kernel's critical path.
+// The FIRST candidate is s = w_2N, the primitive 2N-th root of unity (s^N = -1, usable unless some x_i^N = -1): on that
+// coset every power s^j, (s w_N^a)^k, s^-j is an entry of the 2N-domain's twiddle table, so the scaling kernels do one
+// table lookup and one product per element instead of a power ladder and two products (out[CS_MODE].l[0] = 1).
 constexpr int CS_TAB = 32;
+constexpr int CS_MODE = 2 + 2 * CS_TAB;   // index of the mode word in the shift buffer
 __global__ void __launch_bounds__(256) coset_shift_kernel(const Fr* __restrict__ xs, uint32_t m, uint32_t log_n,
-                                                          Fr seven, Fr seven_inv, Fr gN, Fr* __restrict__ out) {
-    __shared__ int bad;
+                                                          Fr seven, Fr seven_inv, Fr gN, Fr w2n, Fr w2n_inv, uint32_t allow_root,
+                                                          Fr* __restrict__ out) {
+    __shared__ int bad, bad_root;
     __shared__ Fr s_sh[2];
     Fr cand = Fr::one();
     Fr s = Fr::one(), sinv = Fr::one();
+    const Fr minus_one = Fr::one().neg();
+    uint32_t mode = 0;
     for (uint32_t k = 1; k <= m + 1; k++) {
         cand = cand * gN;  // (7^k)^N
         s = s * seven;
         sinv = sinv * seven_inv;
-        if (threadIdx.x == 0) bad = 0;
+        if (threadIdx.x == 0) { bad = 0; bad_root = 0; }
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
             Fr v = xs[i];
             for (uint32_t t = 0; t < log_n; t++) v = v.sqr();
             if (v == cand) bad = 1;
+            if (v == minus_one) bad_root = 1;
         }
         __syncthreads();
-        int b = bad;
+        const int b = bad, br = bad_root;
         __syncthreads();
+        if (k == 1 && allow_root && !br) {   // the root-of-unity coset is free of roots of Z
+            s = w2n;
+            sinv = w2n_inv;
+            mode = 1;
+            break;
+        }
         if (!b) break;
     }
     if (threadIdx.x == 0) {
         out[0] = s;
         out[1] = sinv;
+        Fr md = Fr::zero();
+        md.l[0] = mode;
+        out[CS_MODE] = md;
         s_sh[0] = s;
         s_sh[1] = sinv;
     }
@@ -247,12 +264,25 @@ KZG_DI Fr pow_from_table(const Fr* __restrict__ tab, size_t e) {
 constexpr int CS_CHUNK = 16;
 // dst[j] = (a[j] - b[j]) * s^j for j < len (a has na entries, b has nb entries; missing entries are zero),
 // and 0 for len <= j < N.
+// tw2 = half twiddle table of the 2N-point domain (w_2N^e, e < N); used when the shift is w_2N (mode word = 1)
 __global__ void coset_scale_kernel(const Fr* __restrict__ a, size_t na, const Fr* __restrict__ b, size_t nb, size_t len,
-                                   size_t N, const Fr* __restrict__ shift, Fr* __restrict__ dst) {
+                                   size_t N, const Fr* __restrict__ shift, const Fr* __restrict__ tw2, Fr* __restrict__ dst) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t lo = t * CS_CHUNK;
     if (lo >= N) return;
     size_t hi = min(lo + CS_CHUNK, N);
+    if (shift[CS_MODE].l[0]) {   // s = w_2N: s^j is a table entry
+        for (size_t j = lo; j < hi; j++) {
+            Fr v = Fr::zero();
+            if (j < len) {
+                if (j < na) v = b_ld(&a[j]);
+                if (b && j < nb) v = v - b_ld(&b[j]);
+                v = v * b_ld(&tw2[j]);
+            }
+            b_st(&dst[j], v);
+        }
+        return;
+    }
     const Fr s = shift[0];
     Fr pw = (lo < len) ? pow_from_table(shift + 2, lo) : Fr::zero();
     for (size_t j = lo; j < hi; j++) {
@@ -268,11 +298,16 @@ __global__ void coset_scale_kernel(const Fr* __restrict__ a, size_t na, const Fr
 }
 
 // dst[j] -= r[j] * s^j for j < lr (the interpolant's share of the numerator, applied after the p-only scaling)
-__global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restrict__ r, size_t lr, const Fr* __restrict__ shift) {
+__global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restrict__ r, size_t lr, const Fr* __restrict__ shift,
+                                        const Fr* __restrict__ tw2) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t lo = t * CS_CHUNK;
     if (lo >= lr) return;
     size_t hi = min(lo + CS_CHUNK, lr);
+    if (shift[CS_MODE].l[0]) {
+        for (size_t j = lo; j < hi; j++) b_st(&dst[j], b_ld(&dst[j]) - b_ld(&r[j]) * b_ld(&tw2[j]));
+        return;
+    }
     const Fr s = shift[0];
     Fr pw = pow_from_table(shift + 2, lo);
     for (size_t j = lo; j < hi; j++) {
@@ -287,12 +322,23 @@ __global__ void coset_sub_scaled_kernel(Fr* __restrict__ dst, const Fr* __restri
 // butterfly stages per element.  tw = half twiddle table of the N-point domain.
 __global__ void __launch_bounds__(128) coset_fill_z_kernel(const Fr* __restrict__ Z, uint32_t m, const Fr* __restrict__ tw,
                                                            uint32_t log_cn, uint32_t log_m, const Fr* __restrict__ shift,
-                                                           Fr* __restrict__ dst) {
+                                                           const Fr* __restrict__ tw2, Fr* __restrict__ dst) {
     const uint32_t chunks = (m + 1 + CS_CHUNK - 1) / CS_CHUNK;
     const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t a = idx / chunks;
     if (a >> log_cn) return;
     const uint32_t k0 = (uint32_t)(idx % chunks) * CS_CHUNK, k1 = min(k0 + CS_CHUNK, m + 1);
+    if (shift[CS_MODE].l[0]) {   // s w_N^a = w_2N^(2a+1): its k-th power is the table entry (2a+1) k mod 2N (minus it above N)
+        const uint32_t log_n = log_cn + log_m;
+        const uint64_t N = (uint64_t)1 << log_n;
+        for (uint32_t k = k0; k < k1; k++) {
+            const uint64_t e = ((2 * (uint64_t)a + 1) * k) & (2 * N - 1);
+            Fr w = b_ld(&tw2[e & (N - 1)]);
+            Fr v = b_ld(&Z[k]) * w;
+            b_st(&dst[(a << log_m) + k], e >= N ? v.neg() : v);
+        }
+        return;
+    }
     const Fr base = shift[0] * b_ld(&tw[a]);   // a < N/M <= N/2
     Fr pw = base.pow_u64(k0);
     for (uint32_t k = k0; k < k1; k++) {
@@ -345,11 +391,25 @@ __global__ void __launch_bounds__(PD_THREADS, KZG_PD_MINB) pointwise_div_kernel(
 
 // psi[j] = q[j] * s^-j for j < keep; flag |= 1 if any q[j] != 0 for keep <= j < N
 __global__ void coset_unscale_kernel(const Fr* __restrict__ q, size_t N, size_t keep, const Fr* __restrict__ shift,
-                                     Fr* __restrict__ psi, int* __restrict__ flag) {
+                                     const Fr* __restrict__ tw2, Fr* __restrict__ psi, int* __restrict__ flag) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t lo = t * CS_CHUNK;
     if (lo >= N) return;
     size_t hi = min(lo + CS_CHUNK, N);
+    if (shift[CS_MODE].l[0]) {   // s = w_2N: s^-j = w_2N^(2N - j) = -w_2N^(N - j) for 0 < j < N
+        int nz = 0;
+        for (size_t j = lo; j < hi; j++) {
+            Fr v = b_ld(&q[j]);
+            if (j < keep) {
+                if (j) v = (v * b_ld(&tw2[N - j])).neg();
+                b_st(&psi[j], v);
+            } else if (!v.is_zero()) {
+                nz = 1;
+            }
+        }
+        if (nz) atomicOr(flag, 1);
+        return;
+    }
     const Fr sinv = shift[1];
     Fr pw = (lo < keep) ? pow_from_table(shift + 2 + CS_TAB, lo) : Fr::zero();
     int nz = 0;
@@ -451,7 +511,7 @@ size_t batch_div_workspace_bytes(size_t n, size_t m) {
     if (m == 1 && L < 2) L = 2;
     uint32_t log_n = 0;
     while (((size_t)1 << log_n) < L) log_n++;
-    return 3 * al(((size_t)32) << log_n) + al((2 + 2 * CS_TAB) * sizeof(Fr)) + 256;
+    return 3 * al(((size_t)32) << log_n) + al((3 + 2 * CS_TAB) * sizeof(Fr)) + 256;
 }
 
 // psi = (p - r) div Z.  d_p: n coefficients; d_r: lr coefficients; d_Z: m+1 coefficients (monic).
@@ -482,6 +542,7 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
     Fr* Zb = (Fr*)(w + nb);
     Fr* tmp = (Fr*)(w + 2 * nb);
     Fr* shift = (Fr*)(w + 3 * nb);
+    const Fr* tw2 = nullptr;   // half twiddle table of the 2N-point domain (root-of-unity coset)
     {
         static const FrHost h7 = fr_host_from_u64(7), h7inv = fr_host_inv(h7);
         const FrHost hgN = fr_host_pow(h7, (uint64_t)1 << log_n);   // 7^N (log_n < 32)
@@ -489,18 +550,29 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
         memcpy(seven.l, h7.l, 32);
         memcpy(seven_inv.l, h7inv.l, 32);
         memcpy(gN.l, hgN.l, 32);
-        coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, seven, seven_inv, gN, shift);
+        // first candidate: the 2N-th root of unity (needs the 2N-domain's twiddle table: log_n + 1 <= 31)
+        const bool allow_root = log_n + 1 < 32 && !getenv("KZGB_BATCH_POWER_COSET");
+        Fr w2n = seven, w2n_inv = seven;
+        if (allow_root) {
+            int st2 = ntt_get_twiddles(log_n + 1, stream, &tw2);
+            if (st2) return st2;
+            const FrHost hw = fr_host_domain_omega(log_n + 1), hwi = fr_host_inv(hw);
+            memcpy(w2n.l, hw.l, 32);
+            memcpy(w2n_inv.l, hwi.l, 32);
+        }
+        coset_shift_kernel<<<1, 256, 0, stream>>>(d_xs, (uint32_t)m, log_n, seven, seven_inv, gN, w2n, w2n_inv, allow_root ? 1u : 0u,
+                                                  shift);
     }
     KZG_LAUNCHED();
     unsigned gsz = div_up((N + CS_CHUNK - 1) / CS_CHUNK, 128);
     if (r_ready) {
-        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, nullptr, 0, L, N, shift, A);      // p * s^j alone
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, nullptr, 0, L, N, shift, tw2, A);      // p * s^j alone
         KZG_LAUNCHED();
         KZG_CUDA(cudaStreamWaitEvent(stream, r_ready, 0));
-        coset_sub_scaled_kernel<<<div_up((lr + CS_CHUNK - 1) / CS_CHUNK, 128), 128, 0, stream>>>(A, d_r, lr, shift);
+        coset_sub_scaled_kernel<<<div_up((lr + CS_CHUNK - 1) / CS_CHUNK, 128), 128, 0, stream>>>(A, d_r, lr, shift, tw2);
         KZG_LAUNCHED();
     } else {
-        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, A);
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_p, n, d_r, lr, L, N, shift, tw2, A);
         KZG_LAUNCHED();
     }
     uint32_t log_m = 1;
@@ -514,10 +586,10 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
         if (st) return st;
         KZG_CUDA(cudaMemsetAsync(Zb, 0, N * sizeof(Fr), stream));
         const size_t work = ((size_t)1 << log_cn) * ((m + 1 + CS_CHUNK - 1) / CS_CHUNK);
-        coset_fill_z_kernel<<<div_up(work, 128), 128, 0, stream>>>(d_Z, (uint32_t)m, twN, log_cn, log_m, shift, Zb);
+        coset_fill_z_kernel<<<div_up(work, 128), 128, 0, stream>>>(d_Z, (uint32_t)m, twN, log_cn, log_m, shift, tw2, Zb);
         KZG_LAUNCHED();
     } else {
-        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, Zb);
+        coset_scale_kernel<<<gsz, 128, 0, stream>>>(d_Z, m + 1, nullptr, 0, m + 1, N, shift, tw2, Zb);
         KZG_LAUNCHED();
     }
     st = ntt_run(A, tmp, log_n, false, stream);
@@ -531,7 +603,7 @@ int batch_divide_run(const Fr* d_p, size_t n, const Fr* d_r, size_t lr, const Fr
     st = ntt_run(A, tmp, log_n, true, stream);
     if (st) return st;
     size_t keep = L - m;
-    coset_unscale_kernel<<<gsz, 128, 0, stream>>>(A, N, keep, shift, d_psi, d_flag);
+    coset_unscale_kernel<<<gsz, 128, 0, stream>>>(A, N, keep, shift, tw2, d_psi, d_flag);
     KZG_LAUNCHED();
     *psi_len = keep;
     return KZGB_OK;

@@ -325,6 +325,41 @@ def test_inversion_three_ways(gpu, cpu):
         assert O.fq_from_mont_limbs(g[k]) == (pow(x, -1, P) if x else 0)
 
 
+@pytest.mark.parametrize("case", ["root_coset_blocked", "root_and_first_power_blocked", "free"])
+def test_batched_witness_coset_choice(gpu, cpu, case):
+    """The exact division by Z runs on a coset s*H that must avoid the opening points.  The first candidate is the
+    2N-th root of unity (s^N = -1: every scaling factor is a twiddle-table entry); an x_i with x_i^N = -1 forces the
+    fall-back to powers of 7, an additional x_j on 7*H forces 49*H.  The witness and the interpolant must not change."""
+    from kzg_b200 import scalar as S
+    s_i = O.fr_stream(69, 1)[0]
+    n = 256
+    srs = gpu.srs_generate(0, S.fr(s_i), n)
+    p_i = O.fr_stream(42, n)
+    omega = O.compute_omega(n)[2]
+    w2n = O.compute_omega(2 * n)[2]
+    assert pow(w2n, n, R) == R - 1
+    xs_i = O.fr_stream(7, 6)
+    if case != "free":
+        xs_i = [w2n * pow(omega, 3, R) % R] + xs_i          # on the coset w_2N * H: x^N = -1
+    if case == "root_and_first_power_blocked":
+        xs_i = [7 * pow(omega, 5, R) % R] + xs_i             # on 7 * H as well
+    poly = O.Polynomial.new(p_i)
+    ys_i = [poly.eval(x) for x in xs_i]
+    st, r, w = gpu.witness_batched(srs, S.fr_vec(p_i), S.fr_vec(xs_i), S.fr_vec(ys_i))
+    tree = O.SubProductTree.new_from_points(xs_i)
+    ref = O.Polynomial.lagrange_interpolation_with_tree(xs_i, ys_i, tree)
+    z = 1
+    for x in xs_i:
+        z = z * (s_i - x) % R
+    k = (poly.eval(s_i) - ref.eval(s_i)) * pow(z, -1, R) % R
+    assert st == 0 and S.fr_vec_int(r) == ref.coeffs[: ref.degree + 1]
+    assert (w == cpu.g1_to_affine(cpu.g1_mul(cpu.g1_generator(), S.fr(k)))[0]).all()     # closed form ((p - r)/Z)(s) * G
+    # a wrong y must still be detected on every coset
+    ys_bad = list(ys_i)
+    ys_bad[1] = (ys_bad[1] + 1) % R
+    assert gpu.witness_batched(srs, S.fr_vec(p_i), S.fr_vec(xs_i), S.fr_vec(ys_bad))[0] == gpu.KZGB_POINT_NOT_ON_POLYNOMIAL
+
+
 def test_shutdown_releases_handles_and_allows_reinit():
     """kzgb_shutdown with live handles (own process): their device memory is released, a later destroy only frees the
     host side, and a re-initialised library works again (per-device kernel attributes and caches are rebuilt)."""
