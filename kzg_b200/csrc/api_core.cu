@@ -222,10 +222,22 @@ cudaError_t upload_async(void* dst, const void* src, size_t bytes, cudaStream_t 
         }
         errs[t] = e;
     };
+    // a thread that cannot be started (resource limits) leaves its share to the calling thread: never unwind through the C ABI
     std::thread th[RELAY_MAX_THREADS];
-    for (int t = 1; t < T; t++) th[t] = std::thread(work, t);
+    bool started[RELAY_MAX_THREADS] = {false};
+    for (int t = 1; t < T; t++) {
+        try {
+            th[t] = std::thread(work, t);
+            started[t] = true;
+        } catch (...) {
+            started[t] = false;
+        }
+    }
     work(0);
-    for (int t = 1; t < T; t++) th[t].join();
+    for (int t = 1; t < T; t++) {
+        if (started[t]) th[t].join();
+        else work(t);
+    }
     for (int t = 0; t < T; t++)
         if (errs[t] != cudaSuccess) return errs[t];
     return cudaSuccess;   // the source has been read; the last slices may still be in flight on `st`
@@ -278,10 +290,22 @@ cudaError_t download_async(void* dst, const void* src, size_t bytes, cudaStream_
         }
         errs[t] = e;
     };
+    // a thread that cannot be started (resource limits) leaves its share to the calling thread: never unwind through the C ABI
     std::thread th[RELAY_MAX_THREADS];
-    for (int t = 1; t < T; t++) th[t] = std::thread(work, t);
+    bool started[RELAY_MAX_THREADS] = {false};
+    for (int t = 1; t < T; t++) {
+        try {
+            th[t] = std::thread(work, t);
+            started[t] = true;
+        } catch (...) {
+            started[t] = false;
+        }
+    }
     work(0);
-    for (int t = 1; t < T; t++) th[t].join();
+    for (int t = 1; t < T; t++) {
+        if (started[t]) th[t].join();
+        else work(t);
+    }
     for (int t = 0; t < T; t++)
         if (errs[t] != cudaSuccess) return errs[t];
     return cudaSuccess;
