@@ -932,6 +932,9 @@ struct Fe {
         for (int i = 0; i < N; i++) { u[i] = P::mod(i); v[i] = l[i]; r[i] = 0; s[i] = 0; }
         s[0] = 1;
         int k = 0;
+        // Each pass removes ALL trailing zero bits at once (up to 31): a subtraction of two odd numbers is always followed
+        // by at least one halving, so the subtract step and the halvings after it are one iteration.  Same sequence of
+        // operations as the bit-at-a-time loop (same k, same r, s), about half as many trips.
 #pragma unroll 1
         for (;;) {
             uint32_t vz = 0;
@@ -939,29 +942,37 @@ struct Fe {
             for (int i = 0; i < N; i++) vz |= v[i];
             if (vz == 0) break;
             if ((u[0] & 1) == 0) {
-                shr1(u); shl1(s);
+                const int c = tz31(u[0]);
+                shrk(u, c); shlk(s, c);
+                k += c;
             } else if ((v[0] & 1) == 0) {
-                shr1(v); shl1(r);
+                const int c = tz31(v[0]);
+                shrk(v, c); shlk(r, c);
+                k += c;
             } else {
                 uint32_t t[N];
                 t[0] = sub_cc(v[0], u[0]);
 #pragma unroll
                 for (int i = 1; i < N; i++) t[i] = subc_cc(v[i], u[i]);
                 uint32_t borrow = subc(0, 0);
-                if (borrow) {  // u > v:  u = (u - v)/2, r = r + s, s = 2s
+                if (borrow) {  // u > v:  u = (u - v) / 2^c, r = r + s, s = 2^c s
                     u[0] = sub_cc(0, t[0]);
 #pragma unroll
                     for (int i = 1; i < N; i++) u[i] = subc_cc(0, t[i]);
-                    shr1(u);
-                    addn(r, s); shl1(s);
-                } else {       // v >= u: v = (v - u)/2, s = s + r, r = 2r
+                    const int c = tz31(u[0]);
+                    shrk(u, c);
+                    addn(r, s); shlk(s, c);
+                    k += c;
+                } else {       // v >= u: v = (v - u) / 2^c, s = s + r, r = 2^c r
+                    uint32_t tzv = 0;
 #pragma unroll
-                    for (int i = 0; i < N; i++) v[i] = t[i];
-                    shr1(v);
-                    addn(s, r); shl1(r);
+                    for (int i = 0; i < N; i++) { v[i] = t[i]; tzv |= t[i]; }
+                    const int c = tzv ? tz31(v[0]) : 1;   // v == u: exactly one halving, as in the bit-at-a-time loop
+                    shrk(v, c);
+                    addn(s, r); shlk(r, c);
+                    k += c;
                 }
             }
-            k++;
         }
         // r < 2*MOD holds a^-1 * 2^k up to sign: r = MOD - (r mod MOD)
         Fe x;
@@ -1146,6 +1157,25 @@ struct Fe {
 #pragma unroll
         for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], 1);
         a[0] <<= 1;
+    }
+    // trailing zero bits of a non-zero-or-zero low limb, capped at 31 (a zero limb: 31 -- the value stays even)
+    KZG_DI static int tz31(uint32_t w) {
+#if defined(KZG_HOST_EMU) && !defined(__CUDA_ARCH__)
+        const int c = w ? __builtin_ctz(w) : 31;
+#else
+        const int c = w ? (__ffs((int)w) - 1) : 31;
+#endif
+        return c > 31 ? 31 : c;
+    }
+    KZG_DI static void shrk(uint32_t* a, int c) {   // a >>= c, 0 < c < 32
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) a[i] = __funnelshift_r(a[i], a[i + 1], c);
+        a[N - 1] >>= c;
+    }
+    KZG_DI static void shlk(uint32_t* a, int c) {   // a <<= c, 0 < c < 32
+#pragma unroll
+        for (int i = N - 1; i > 0; i--) a[i] = __funnelshift_l(a[i - 1], a[i], c);
+        a[0] <<= c;
     }
     KZG_DI static void addn(uint32_t* a, const uint32_t* b) {
         a[0] = add_cc(a[0], b[0]);
